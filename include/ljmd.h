@@ -1,0 +1,190 @@
+/*
+ * ljmd.h -- C ABI of the B200-native Lennard-Jones MD hot path (libljmd.so).
+ *
+ * Drop-in boundary for the reference's two hot-path module procedures
+ * (Ledicia/Molecular-Dynamics-Simulation---Lennard-Jones-monoatomic-fluid; citations are
+ * file:line relative to the reference's scripts/ directory):
+ *
+ *   compute_lj_potential_energy(params, state, epot, d_epot, dd_epot)
+ *                                              physics/lj_potential_energy.f90:46-52
+ *   verlet_step(params, state, epot, ekin, d_epot, dd_epot)
+ *                                              physics/verlet.f90:41-48
+ *
+ * The reference has no FFI layer (plain Fortran module procedures).  INTEGRATION.md shows the
+ * ISO_C_BINDING replacement modules that keep those names/dummy lists and call the functions
+ * below.  All reals are IEEE binary64, all integers int32 (base/define_precision.f90:14,17).
+ *
+ * Conventions
+ *   - Every function returns an int status: LJMD_OK (0) or an LJMD_ERR_* code.  The reference
+ *     `stop`s with a message instead; ljmd_last_error() returns the equivalent text so a shim
+ *     can reproduce that behaviour.
+ *   - The library never retains host pointers after a call returns and never frees them.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     LJMD_ERR_CUDA.
+ *   - Host-pointer functions are synchronous.  One host thread per context.
+ */
+#ifndef LJMD_H
+#define LJMD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LJMD_VERSION 100
+
+/* Mirror of type(sim_params), base/md_types.f90:27-50, in gfortran's de-facto layout:
+ * offsets 0,4,8,16,...,88; sizeof == 96. */
+typedef struct ljmd_params {
+    int32_t n;              /* number of particles                      md_types.f90:29 */
+    int32_t num_cells;      /* FCC cells per edge                       md_types.f90:30 */
+    double box_length;      /* L                                        md_types.f90:33 */
+    double inv_box_length;  /* 1/L                                      md_types.f90:34 */
+    double volume;          /* L**3                                     md_types.f90:35 */
+    double density;         /* n / volume                               md_types.f90:36 */
+    double dt;              /* time step                                md_types.f90:39 */
+    double dt_half;         /* 0.5*dt                                   md_types.f90:40 */
+    double dt_square_half;  /* 0.5*dt*dt                                md_types.f90:41 */
+    double rc;              /* cutoff radius                            md_types.f90:44 */
+    double rc_square;       /* rc*rc                                    md_types.f90:45 */
+    double length_scale;    /* legacy, unused on the hot path           md_types.f90:48 */
+    double inv_length_scale;/*                                          md_types.f90:49 */
+} ljmd_params;
+
+/* Status codes.  1..5 mirror the `stop` guards of lj_potential_energy.f90:77-81; 6 mirrors the
+ * allocated() guards (:82, verlet.f90:52); 7,8 mirror md_types.f90:152,161. */
+enum {
+    LJMD_OK = 0,
+    LJMD_ERR_N = 1,            /* params%n must be > 0 */
+    LJMD_ERR_BOX = 2,          /* params%box_length must be > 0 */
+    LJMD_ERR_VOLUME = 3,       /* params%volume must be > 0 */
+    LJMD_ERR_RC = 4,           /* params%rc must be > 0 */
+    LJMD_ERR_RC_SQUARE = 5,    /* params%rc_square must be > 0 */
+    LJMD_ERR_NULL = 6,         /* a required array/pointer is NULL ("not allocated") */
+    LJMD_ERR_RC_HALF_BOX = 7,  /* rc must be < L/2 (minimum image) */
+    LJMD_ERR_DT = 8,           /* dt must be > 0 */
+    LJMD_ERR_ARG = 9,          /* invalid option / argument */
+    LJMD_ERR_UNSUPPORTED = 10, /* e.g. cell list requested with fewer than 3 cells per edge */
+    LJMD_ERR_CUDA = 100,       /* CUDA runtime/driver error (no device, launch failure, ...) */
+    LJMD_ERR_NOMEM = 101
+};
+
+/* Force method of a context. */
+enum {
+    LJMD_METHOD_AUTO = 0,     /* all-pairs unless floor(L/rc) >= 4 and N >= 16384 */
+    LJMD_METHOD_ALLPAIRS = 1, /* O(N^2), the reference's algorithm */
+    LJMD_METHOD_CELLS = 2     /* counting-sort cell list + 27-cell stencil (no reference counterpart) */
+};
+
+/* Context flags. */
+enum {
+    LJMD_FLAG_TRACK_UNWRAPPED = 1 /* keep ru(t) on the device, md_simulation_program.f90:339-353 */
+};
+
+typedef struct ljmd_options {
+    int32_t method;    /* LJMD_METHOD_* */
+    int32_t device;    /* CUDA device ordinal; -1 = the calling thread's current device */
+    int32_t nreplicas; /* >= 1 independent systems sharing `params`; arrays are [nreplicas][n] */
+    int32_t flags;     /* LJMD_FLAG_* */
+} ljmd_options;
+
+typedef struct ljmd_ctx ljmd_ctx;
+
+/* ----------------------------------------------------------------------------------------
+ * Library / diagnostics
+ * -------------------------------------------------------------------------------------- */
+int ljmd_version(void);
+/* Text of the last error raised on the calling thread ("" if none). */
+const char *ljmd_last_error(void);
+/* Number of CUDA devices visible (0 if none / no driver). */
+int ljmd_device_count(void);
+
+/* ----------------------------------------------------------------------------------------
+ * Parameters: init_params + compute_derived_params, base/md_types.f90:105-169.
+ * Returns LJMD_ERR_BOX / _RC / _RC_HALF_BOX / _DT where the reference stops (:143,150,153,161).
+ * -------------------------------------------------------------------------------------- */
+int ljmd_params_init(ljmd_params *p, int32_t n, double box_length, double dt, double rc,
+                     int32_t num_cells);
+
+/* ----------------------------------------------------------------------------------------
+ * Stateless drop-in pair (host pointers, length params->n each; copies in and out every call).
+ * -------------------------------------------------------------------------------------- */
+
+/* Replaces compute_lj_potential_energy, physics/lj_potential_energy.f90:46-225.
+ * in: rx,ry,rz.  out: ax,ay,az (overwritten), epot, d_epot, dd_epot (tail corrections included,
+ * :205-223). */
+int ljmd_compute_lj(const ljmd_params *params, const double *rx, const double *ry,
+                    const double *rz, double *ax, double *ay, double *az, double *epot,
+                    double *d_epot, double *dd_epot);
+
+/* Replaces verlet_step, physics/verlet.f90:41-97.  All nine arrays are updated in place. */
+int ljmd_verlet_step(const ljmd_params *params, double *rx, double *ry, double *rz, double *vx,
+                     double *vy, double *vz, double *ax, double *ay, double *az, double *epot,
+                     double *ekin, double *d_epot, double *dd_epot);
+
+/* Release the cached device workspace the two functions above keep between calls. */
+int ljmd_compat_release(void);
+
+/* ----------------------------------------------------------------------------------------
+ * Device-resident API (state stays in HBM between calls).
+ * -------------------------------------------------------------------------------------- */
+int ljmd_ctx_create(const ljmd_params *params, const ljmd_options *opts, ljmd_ctx **out);
+int ljmd_ctx_destroy(ljmd_ctx *ctx);
+
+/* Host -> device.  Any pointer may be NULL (that array is left unchanged).  Each array holds
+ * nreplicas*n doubles.  Uploading positions also resets ru := r when unwrapped tracking is on
+ * (md_simulation_program.f90:226-231). */
+int ljmd_ctx_upload(ljmd_ctx *ctx, const double *rx, const double *ry, const double *rz,
+                    const double *vx, const double *vy, const double *vz, const double *ax,
+                    const double *ay, const double *az);
+/* Device -> host.  Any pointer may be NULL. */
+int ljmd_ctx_download(ljmd_ctx *ctx, double *rx, double *ry, double *rz, double *vx, double *vy,
+                      double *vz, double *ax, double *ay, double *az);
+/* Unwrapped coordinates ru (needs LJMD_FLAG_TRACK_UNWRAPPED). */
+int ljmd_ctx_download_unwrapped(ljmd_ctx *ctx, double *rux, double *ruy, double *ruz);
+
+/* compute_lj_potential_energy on the resident state (the t=0 call,
+ * md_simulation_program.f90:236).  obs3 = {epot, d_epot, dd_epot} per replica (3*nreplicas). */
+int ljmd_ctx_compute_forces(ljmd_ctx *ctx, double *obs3);
+
+/* nsteps x verlet_step (+ the unwrapped update if tracked) with no host round-trip.
+ * obs4 = {epot, ekin, d_epot, dd_epot} of the LAST step, per replica (4*nreplicas); may be NULL.
+ */
+int ljmd_ctx_step(ljmd_ctx *ctx, int32_t nsteps, double *obs4);
+
+/* As ljmd_ctx_step, but records the 4 observables of every step: series[nsteps][nreplicas][4]. */
+int ljmd_ctx_step_series(ljmd_ctx *ctx, int32_t nsteps, double *series);
+
+/* Driver-side kinetic energy 0.5*sum(vx^2+vy^2+vz^2) (md_simulation_program.f90:238-240),
+ * per replica. */
+int ljmd_ctx_kinetic_energy(ljmd_ctx *ctx, double *ekin);
+
+/* Introspection used by tests and benchmarks. */
+int ljmd_ctx_method(const ljmd_ctx *ctx);          /* resolved LJMD_METHOD_* */
+int ljmd_ctx_cells_per_edge(const ljmd_ctx *ctx);  /* 0 for all-pairs */
+/* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */
+int64_t ljmd_ctx_launch_count(const ljmd_ctx *ctx);
+/* Device time (CUDA events on the context's stream, first kernel to last kernel) of the most
+ * recent ljmd_ctx_step call, in milliseconds. */
+int ljmd_ctx_last_step_ms(const ljmd_ctx *ctx, double *ms);
+/* Device time of the force kernel(s) accumulated since the last reset, in milliseconds, and the
+ * number of force evaluations it covers.  Timing is only recorded when enabled. */
+int ljmd_ctx_force_timing(ljmd_ctx *ctx, int32_t enable, double *ms_total, int64_t *n_evals);
+
+/* Cell-list integer state of the last force evaluation (LJMD_METHOD_CELLS only):
+ * cell_of_atom[n] (cell id of each atom, original numbering), cell_start[ncell^3+1],
+ * order[n] (original index of the k-th atom in cell-sorted order).  Any pointer may be NULL. */
+int ljmd_ctx_download_cells(ljmd_ctx *ctx, int32_t *cell_of_atom, int32_t *cell_start,
+                            int32_t *order);
+/* Unordered candidate pairs distance-tested / in-cutoff pairs of the last force evaluation. */
+int ljmd_ctx_pair_counts(ljmd_ctx *ctx, int64_t *n_candidates, int64_t *n_in_cutoff);
+
+/* Measured FP64 FMA throughput of the device the context lives on (register-resident DFMA
+ * chains), in TFLOP/s; the roofline denominator for the all-pairs kernel. */
+int ljmd_measure_fp64_peak(int32_t device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LJMD_H */

@@ -1,0 +1,334 @@
+"""B200-native Lennard-Jones MD hot path: host-side mirror of the reference interface.
+
+This package is a thin ctypes layer over ``lib/libljmd.so`` (hand-written sm_100a CUDA behind
+the C ABI declared in ``include/ljmd.h``).  It mirrors the reference's module procedures
+
+* ``compute_lj_potential_energy(params, state, epot, d_epot, dd_epot)``
+  (/root/reference/scripts/physics/lj_potential_energy.f90:46)
+* ``verlet_step(params, state, epot, ekin, d_epot, dd_epot)``
+  (/root/reference/scripts/physics/verlet.f90:41)
+* ``init_params`` / ``init_state`` (/root/reference/scripts/base/md_types.f90:105,175)
+
+with the same argument meaning and error behaviour (a reference ``stop '<msg>'`` becomes an
+:class:`LjmdError` carrying the same message), plus the device-resident :class:`Context`.
+
+There is NO CPU fallback here: if the CUDA library is missing or no GPU is present, compute
+calls raise.  The directory name contains '-' so import it with
+``importlib.import_module("molecular-dynamics-simulation---lennard-jones-monoatomic-fluid_b200")``
+or through the ``ljmd_b200`` alias module at the repository root.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libljmd.so")
+
+METHOD_AUTO, METHOD_ALLPAIRS, METHOD_CELLS = 0, 1, 2
+FLAG_TRACK_UNWRAPPED = 1
+
+ERR_NAMES = {
+    1: "LJMD_ERR_N", 2: "LJMD_ERR_BOX", 3: "LJMD_ERR_VOLUME", 4: "LJMD_ERR_RC",
+    5: "LJMD_ERR_RC_SQUARE", 6: "LJMD_ERR_NULL", 7: "LJMD_ERR_RC_HALF_BOX", 8: "LJMD_ERR_DT",
+    9: "LJMD_ERR_ARG", 10: "LJMD_ERR_UNSUPPORTED", 100: "LJMD_ERR_CUDA", 101: "LJMD_ERR_NOMEM",
+}
+
+
+class LjmdError(RuntimeError):
+    """Raised where the reference would ``stop``; ``code`` is the C-ABI status."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[{ERR_NAMES.get(code, code)}] {message}")
+        self.code = code
+        self.message = message
+
+
+class SimParams(C.Structure):
+    """type(sim_params), base/md_types.f90:27-50 (same field names, 96 bytes)."""
+
+    _fields_ = [
+        ("n", C.c_int32),
+        ("num_cells", C.c_int32),
+        ("box_length", C.c_double),
+        ("inv_box_length", C.c_double),
+        ("volume", C.c_double),
+        ("density", C.c_double),
+        ("dt", C.c_double),
+        ("dt_half", C.c_double),
+        ("dt_square_half", C.c_double),
+        ("rc", C.c_double),
+        ("rc_square", C.c_double),
+        ("length_scale", C.c_double),
+        ("inv_length_scale", C.c_double),
+    ]
+
+
+class _Options(C.Structure):
+    _fields_ = [("method", C.c_int32), ("device", C.c_int32), ("nreplicas", C.c_int32),
+                ("flags", C.c_int32)]
+
+
+_DP = C.POINTER(C.c_double)
+_IP = C.POINTER(C.c_int32)
+_lib: Optional[C.CDLL] = None
+
+# Every symbol include/ljmd.h declares (tests check that the library exports all of them).
+ABI_SYMBOLS = [
+    "ljmd_version", "ljmd_last_error", "ljmd_device_count", "ljmd_params_init",
+    "ljmd_compute_lj", "ljmd_verlet_step", "ljmd_compat_release", "ljmd_ctx_create",
+    "ljmd_ctx_destroy", "ljmd_ctx_upload", "ljmd_ctx_download", "ljmd_ctx_download_unwrapped",
+    "ljmd_ctx_compute_forces", "ljmd_ctx_step", "ljmd_ctx_step_series",
+    "ljmd_ctx_kinetic_energy", "ljmd_ctx_method", "ljmd_ctx_cells_per_edge",
+    "ljmd_ctx_launch_count", "ljmd_ctx_last_step_ms", "ljmd_ctx_force_timing", "ljmd_ctx_download_cells",
+    "ljmd_ctx_pair_counts", "ljmd_measure_fp64_peak",
+]
+
+
+def load_library() -> C.CDLL:
+    """Load libljmd.so; fails loudly if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (nvcc, sm_100a).  This package has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.ljmd_last_error.restype = C.c_char_p
+        L.ljmd_ctx_launch_count.restype = C.c_int64
+        L.ljmd_ctx_launch_count.argtypes = [C.c_void_p]
+        L.ljmd_ctx_method.argtypes = [C.c_void_p]
+        L.ljmd_ctx_cells_per_edge.argtypes = [C.c_void_p]
+        L.ljmd_ctx_destroy.argtypes = [C.c_void_p]
+        L.ljmd_params_init.argtypes = [C.POINTER(SimParams), C.c_int32, C.c_double, C.c_double,
+                                       C.c_double, C.c_int32]
+        _lib = L
+    return _lib
+
+
+def _chk(code: int) -> None:
+    if code != 0:
+        raise LjmdError(code, load_library().ljmd_last_error().decode())
+
+
+def _p(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    if a.dtype != np.float64 or not a.flags.c_contiguous:
+        raise TypeError("state arrays must be C-contiguous float64")
+    return a.ctypes.data_as(_DP)
+
+
+def device_count() -> int:
+    return int(load_library().ljmd_device_count())
+
+
+# ---------------------------------------------------------------------------------------------
+# md_types mirror
+# ---------------------------------------------------------------------------------------------
+def init_params(n: int, box_length: float, dt: float, rc: float, num_cells: int = 0) -> SimParams:
+    """init_params + compute_derived_params, base/md_types.f90:105-169."""
+    p = SimParams()
+    _chk(load_library().ljmd_params_init(C.byref(p), n, box_length, dt, rc, num_cells))
+    return p
+
+
+class SimState:
+    """type(sim_state), base/md_types.f90:56-60: nine SoA float64 arrays, zero-initialised
+    (init_state, :175-182)."""
+
+    NAMES = ("rx", "ry", "rz", "vx", "vy", "vz", "ax", "ay", "az")
+
+    def __init__(self, n: int, nreplicas: int = 1):
+        shape = (n,) if nreplicas == 1 else (nreplicas, n)
+        for name in self.NAMES:
+            setattr(self, name, np.zeros(shape, dtype=np.float64))
+
+    def arrays(self):
+        return [getattr(self, k) for k in self.NAMES]
+
+    def copy(self) -> "SimState":
+        s = SimState.__new__(SimState)
+        for k in self.NAMES:
+            setattr(s, k, getattr(self, k).copy())
+        return s
+
+    @classmethod
+    def from_arrays(cls, arrs: Sequence[np.ndarray]) -> "SimState":
+        s = cls.__new__(cls)
+        for k, a in zip(cls.NAMES, arrs):
+            setattr(s, k, np.ascontiguousarray(a, dtype=np.float64))
+        return s
+
+
+def init_state(params: SimParams, nreplicas: int = 1) -> SimState:
+    if params.n <= 0:
+        raise LjmdError(1, "allocate_state(): params%n must be > 0.")
+    return SimState(params.n, nreplicas)
+
+
+# ---------------------------------------------------------------------------------------------
+# Stateless drop-in pair (host arrays in, host arrays out; H2D/D2H inside the call)
+# ---------------------------------------------------------------------------------------------
+def compute_lj_potential_energy(params: SimParams, state: SimState):
+    """physics/lj_potential_energy.f90:46.  Overwrites state.ax/ay/az; returns
+    (epot, d_epot, dd_epot)."""
+    e, d, dd = C.c_double(), C.c_double(), C.c_double()
+    _chk(load_library().ljmd_compute_lj(C.byref(params), _p(state.rx), _p(state.ry), _p(state.rz),
+                                        _p(state.ax), _p(state.ay), _p(state.az), C.byref(e),
+                                        C.byref(d), C.byref(dd)))
+    return e.value, d.value, dd.value
+
+
+def verlet_step(params: SimParams, state: SimState):
+    """physics/verlet.f90:41.  Updates all nine arrays in place; returns
+    (epot, ekin, d_epot, dd_epot)."""
+    e, k, d, dd = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+    _chk(load_library().ljmd_verlet_step(C.byref(params), *[_p(a) for a in state.arrays()],
+                                         C.byref(e), C.byref(k), C.byref(d), C.byref(dd)))
+    return e.value, k.value, d.value, dd.value
+
+
+def compat_release() -> None:
+    _chk(load_library().ljmd_compat_release())
+
+
+def measure_fp64_peak(device: int = -1) -> float:
+    t = C.c_double()
+    _chk(load_library().ljmd_measure_fp64_peak(device, C.byref(t)))
+    return t.value
+
+
+# ---------------------------------------------------------------------------------------------
+# Device-resident context
+# ---------------------------------------------------------------------------------------------
+class Context:
+    """State resident in HBM; ``step(n)`` runs n velocity-Verlet steps with no host round trip."""
+
+    def __init__(self, params: SimParams, method: int = METHOD_AUTO, device: int = -1,
+                 nreplicas: int = 1, flags: int = 0):
+        self._L = load_library()
+        self.params = params
+        self.nreplicas = nreplicas
+        self._h = C.c_void_p()
+        o = _Options(method, device, nreplicas, flags)
+        _chk(self._L.ljmd_ctx_create(C.byref(params), C.byref(o), C.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.ljmd_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def shape(self):
+        n = self.params.n
+        return (n,) if self.nreplicas == 1 else (self.nreplicas, n)
+
+    def upload(self, state: Optional[SimState] = None, **arrays) -> None:
+        if state is not None:
+            arrays = {k: getattr(state, k) for k in SimState.NAMES}
+        ptrs = []
+        for k in SimState.NAMES:
+            a = arrays.get(k)
+            if a is not None and a.size != self.params.n * self.nreplicas:
+                raise ValueError(f"{k}: expected {self.params.n * self.nreplicas} values")
+            ptrs.append(_p(a))
+        _chk(self._L.ljmd_ctx_upload(self._h, *ptrs))
+
+    def download(self, names: Sequence[str] = SimState.NAMES) -> SimState:
+        s = SimState.__new__(SimState)
+        ptrs = []
+        for k in SimState.NAMES:
+            if k in names:
+                a = np.empty(self.shape, dtype=np.float64)
+                setattr(s, k, a)
+                ptrs.append(_p(a))
+            else:
+                setattr(s, k, None)
+                ptrs.append(None)
+        _chk(self._L.ljmd_ctx_download(self._h, *ptrs))
+        return s
+
+    def download_unwrapped(self):
+        ru = [np.empty(self.shape, dtype=np.float64) for _ in range(3)]
+        _chk(self._L.ljmd_ctx_download_unwrapped(self._h, *[_p(a) for a in ru]))
+        return ru
+
+    def compute_forces(self) -> np.ndarray:
+        """compute_lj_potential_energy on the resident state: (epot, d_epot, dd_epot)[replica]."""
+        obs = np.zeros((self.nreplicas, 3))
+        _chk(self._L.ljmd_ctx_compute_forces(self._h, _p(obs)))
+        return obs[0] if self.nreplicas == 1 else obs
+
+    def step(self, nsteps: int = 1) -> np.ndarray:
+        """nsteps x verlet_step; returns (epot, ekin, d_epot, dd_epot)[replica] of the last."""
+        obs = np.zeros((self.nreplicas, 4))
+        _chk(self._L.ljmd_ctx_step(self._h, int(nsteps), _p(obs)))
+        return obs[0] if self.nreplicas == 1 else obs
+
+    def step_series(self, nsteps: int) -> np.ndarray:
+        ser = np.zeros((nsteps, self.nreplicas, 4))
+        _chk(self._L.ljmd_ctx_step_series(self._h, int(nsteps), _p(ser)))
+        return ser[:, 0, :] if self.nreplicas == 1 else ser
+
+    def kinetic_energy(self) -> np.ndarray:
+        k = np.zeros(self.nreplicas)
+        _chk(self._L.ljmd_ctx_kinetic_energy(self._h, _p(k)))
+        return k[0] if self.nreplicas == 1 else k
+
+    @property
+    def method(self) -> int:
+        return int(self._L.ljmd_ctx_method(self._h))
+
+    @property
+    def cells_per_edge(self) -> int:
+        return int(self._L.ljmd_ctx_cells_per_edge(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.ljmd_ctx_launch_count(self._h))
+
+    @property
+    def last_step_ms(self) -> float:
+        """Device time (CUDA events on the context stream) of the last step() call."""
+        ms = C.c_double()
+        _chk(self._L.ljmd_ctx_last_step_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def force_timing(self, enable: bool):
+        """Enable/disable per-launch CUDA-event timing of the force kernel; returns the
+        (total_ms, n_evals) accumulated since the previous call."""
+        ms, ne = C.c_double(), C.c_int64()
+        _chk(self._L.ljmd_ctx_force_timing(self._h, 1 if enable else 0, C.byref(ms), C.byref(ne)))
+        return ms.value, ne.value
+
+    def pair_counts(self):
+        a, b = C.c_int64(), C.c_int64()
+        _chk(self._L.ljmd_ctx_pair_counts(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def download_cells(self):
+        nc = self.cells_per_edge
+        n = self.params.n
+        cell = np.zeros(n, dtype=np.int32)
+        start = np.zeros(nc ** 3 + 1, dtype=np.int32)
+        order = np.zeros(n, dtype=np.int32)
+        _chk(self._L.ljmd_ctx_download_cells(self._h, cell.ctypes.data_as(_IP),
+                                             start.ctypes.data_as(_IP),
+                                             order.ctypes.data_as(_IP)))
+        return cell, start, order

@@ -1,0 +1,53 @@
+// lj_pair.cuh -- the per-pair arithmetic shared by every force kernel.
+//
+// Compiled with -fmad=false.  Each per-pair quantity is computed with exactly the operations,
+// operand order and roundings of the reference loop body
+// (/root/reference/scripts/physics/lj_potential_energy.f90:119-178), so the terms that are
+// summed are bit-identical to the reference's; only the ORDER of the sums differs.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ljmd {
+
+// Minimum image, physics/geometry_pbc.f90:86:  dx - L*dnint(dx*invL).
+// rint (ties-to-even) differs from dnint (ties-away) only when |dx*invL| is exactly k+0.5,
+// where |dx_mic| = L/2 > rc either way (rc < L/2 is enforced, md_types.f90:152), i.e. never
+// for a pair inside the cutoff.  The FMA is exact-equivalent to the reference's separate
+// multiply and subtract whenever L*k is representable (always for |k| <= 2, i.e. for any
+// positions within two boxes of each other; wrapped positions give |k| <= 1).
+__device__ __forceinline__ double mic(double dx, double L, double invL)
+{
+    return fma(-L, rint(dx * invL), dx);
+}
+
+// Squared distance in the reference's order (:129): (dx*dx + dy*dy) + dz*dz, no contraction,
+// so the strict cutoff test r2 < rc2 (:132) takes the same decision as the reference.
+__device__ __forceinline__ double dist2(double dx, double dy, double dz)
+{
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+struct PairTerms {
+    double fx, fy, fz; // force on i (without the factor 24), :148-150
+    double u;          // inv_r12 - inv_r6, :140
+    double du;         // -2*inv_r12 + inv_r6, :143
+    double ddu;        // 26*inv_r12 - 7*inv_r6, :178
+};
+
+__device__ __forceinline__ PairTerms pair_terms(double dx, double dy, double dz, double r2)
+{
+    PairTerms t;
+    const double inv_r2 = 1.0 / r2;                                       // :135 (IEEE division)
+    const double inv_r6 = __dmul_rn(__dmul_rn(inv_r2, inv_r2), inv_r2);   // :136
+    const double inv_r12 = __dmul_rn(inv_r6, inv_r6);                     // :137
+    t.u = __dadd_rn(inv_r12, -inv_r6);                                    // :140
+    t.du = __dadd_rn(__dmul_rn(-2.0, inv_r12), inv_r6);                   // :143
+    const double m = -t.du;
+    t.fx = __dmul_rn(__dmul_rn(m, dx), inv_r2);                           // :148
+    t.fy = __dmul_rn(__dmul_rn(m, dy), inv_r2);                           // :149
+    t.fz = __dmul_rn(__dmul_rn(m, dz), inv_r2);                           // :150
+    t.ddu = __dadd_rn(__dmul_rn(26.0, inv_r12), -__dmul_rn(7.0, inv_r6)); // :178
+    return t;
+}
+
+} // namespace ljmd

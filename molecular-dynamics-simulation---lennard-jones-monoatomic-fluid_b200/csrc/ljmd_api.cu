@@ -1,0 +1,691 @@
+// ljmd_api.cu -- the C ABI of libljmd.so (include/ljmd.h): parameter handling, contexts,
+// host<->device staging, CUDA-graph step driver and the stateless drop-in pair that replaces
+// the reference's compute_lj_potential_energy / verlet_step
+// (/root/reference/scripts/physics/lj_potential_energy.f90:46, physics/verlet.f90:41).
+//
+// There is no CPU fallback in this library: every compute entry point needs a CUDA device.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <mutex>
+#include <new>
+
+#include "ljmd_internal.h"
+
+namespace ljmd {
+
+static thread_local char g_err[512] = {0};
+
+int set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+void clear_error() { g_err[0] = 0; }
+
+// The same guards, in the same order, as lj_potential_energy.f90:77-81 (+ md_types.f90:152).
+static int check_params(const ljmd_params *p, const char *who)
+{
+    if (!p) return set_error(LJMD_ERR_NULL, "%s(): params is NULL.", who);
+    if (p->n <= 0) return set_error(LJMD_ERR_N, "%s(): params%%n must be > 0.", who);
+    if (!(p->box_length > 0.0))
+        return set_error(LJMD_ERR_BOX, "%s(): params%%box_length must be > 0.", who);
+    if (!(p->volume > 0.0))
+        return set_error(LJMD_ERR_VOLUME, "%s(): params%%volume must be > 0.", who);
+    if (!(p->rc > 0.0)) return set_error(LJMD_ERR_RC, "%s(): params%%rc must be > 0.", who);
+    if (!(p->rc_square > 0.0))
+        return set_error(LJMD_ERR_RC_SQUARE, "%s(): params%%rc_square must be > 0.", who);
+    if (p->rc >= 0.5 * p->box_length)
+        return set_error(LJMD_ERR_RC_HALF_BOX,
+                         "%s(): rc (cutoff_radius) must be < L/2 (minimum image convention).", who);
+    return LJMD_OK;
+}
+
+// Tail constants, lj_potential_energy.f90:205-212, in the reference's operation order
+// (integer powers are repeated multiplications; pi from md_types.f90:22).
+static void tail_constants(const ljmd_params &p, double *tu, double *tdu, double *tddu)
+{
+    const double pi = 3.1415926535897932384626433832795;
+    volatile double npd = (double)p.n;
+    volatile double rc3 = (p.rc * p.rc) * p.rc;
+    volatile double rc6 = rc3 * rc3;
+    volatile double tail_factor = 8.0 * pi * (npd * npd) / (p.volume * rc3);
+    *tu = tail_factor * ((1.0 / (3.0 * rc6)) - 1.0) / 3.0;
+    *tdu = 2.0 * tail_factor * (-2.0 / (3.0 * rc6) + 1.0);
+    *tddu = 2.0 * tail_factor * (26.0 / (3.0 * rc6) - 7.0);
+}
+
+static void refresh_constants(ljmd_ctx *c)
+{
+    SimConst &s = c->sc;
+    s.n = c->p.n;
+    s.R = c->R;
+    s.L = c->p.box_length;
+    s.invL = c->p.inv_box_length;
+    s.rc2 = c->p.rc_square;
+    s.dt = c->p.dt;
+    s.dt_half = c->p.dt_half;
+    s.dt_square_half = c->p.dt_square_half;
+    tail_constants(c->p, &s.tail_u, &s.tail_du, &s.tail_ddu);
+}
+
+static void drop_graphs(ljmd_ctx *c)
+{
+    if (c->graph_chunk) { cudaGraphExecDestroy(c->graph_chunk); c->graph_chunk = nullptr; }
+    if (c->graph_one) { cudaGraphExecDestroy(c->graph_one); c->graph_one = nullptr; }
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool active = false;
+    int enter(int dev)
+    {
+        LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+        if (dev != prev) { LJMD_CUDA_CHECK(cudaSetDevice(dev)); active = true; }
+        return LJMD_OK;
+    }
+    ~DeviceGuard() { if (active) cudaSetDevice(prev); }
+};
+
+static int enqueue_force(ljmd_ctx *c)
+{
+    if (c->method == LJMD_METHOD_CELLS) return launch_cells_force(c);
+    return launch_pairs(c);
+}
+
+static int kernels_per_step(const ljmd_ctx *c) { return (c->method == LJMD_METHOD_CELLS) ? 6 : 3; }
+
+static int enqueue_step(ljmd_ctx *c)
+{
+    LJMD_TRY(launch_verlet_pre(c));
+    LJMD_TRY(enqueue_force(c));
+    LJMD_TRY(launch_finalize(c, true));
+    return LJMD_OK;
+}
+
+static int capture_graph(ljmd_ctx *c, int nsteps, cudaGraphExec_t *out)
+{
+    cudaGraph_t g = nullptr;
+    const int64_t saved = c->launches;
+    LJMD_CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = LJMD_OK;
+    for (int s = 0; s < nsteps && rc == LJMD_OK; ++s) rc = enqueue_step(c);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    c->launches = saved; // captured, not executed
+    if (rc != LJMD_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    LJMD_CUDA_CHECK(e);
+    e = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    LJMD_CUDA_CHECK(e);
+    return LJMD_OK;
+}
+
+static int ensure_stage(ljmd_ctx *c)
+{
+    if (!c->h_stage) {
+        const size_t bytes = sizeof(double) * (9 * c->nR + 4 * (size_t)c->R);
+        LJMD_CUDA_CHECK(cudaMallocHost(&c->h_stage, bytes));
+    }
+    return LJMD_OK;
+}
+
+static int set_ctl(ljmd_ctx *c, long long cap, double *series)
+{
+    StepCtl h;
+    h.step = 0;
+    h.series_cap = cap;
+    h.series = series;
+    // small synchronous-with-respect-to-stream copy from pageable memory (24 bytes)
+    LJMD_CUDA_CHECK(cudaMemcpyAsync(c->fw.ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+    LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return LJMD_OK;
+}
+
+static int run_steps(ljmd_ctx *c, int nsteps)
+{
+    if (c->timing) {
+        for (int s = 0; s < nsteps; ++s) {
+            LJMD_TRY(launch_verlet_pre(c));
+            LJMD_CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
+            LJMD_TRY(enqueue_force(c));
+            LJMD_CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
+            LJMD_TRY(launch_finalize(c, true));
+            LJMD_CUDA_CHECK(cudaEventSynchronize(c->ev1));
+            float ms = 0.f;
+            LJMD_CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+            c->force_ms += ms;
+            c->force_evals += 1;
+        }
+        return LJMD_OK;
+    }
+    if (nsteps <= 2) {
+        for (int s = 0; s < nsteps; ++s) LJMD_TRY(enqueue_step(c));
+        return LJMD_OK;
+    }
+    const int G = 32;
+    if (nsteps >= G && !c->graph_chunk) {
+        LJMD_TRY(capture_graph(c, G, &c->graph_chunk));
+        c->graph_chunk_steps = G;
+    }
+    if (!c->graph_one) LJMD_TRY(capture_graph(c, 1, &c->graph_one));
+    int left = nsteps;
+    while (left >= G) {
+        LJMD_CUDA_CHECK(cudaGraphLaunch(c->graph_chunk, c->stream));
+        c->launches += (int64_t)G * kernels_per_step(c);
+        left -= G;
+    }
+    while (left > 0) {
+        LJMD_CUDA_CHECK(cudaGraphLaunch(c->graph_one, c->stream));
+        c->launches += kernels_per_step(c);
+        left -= 1;
+    }
+    return LJMD_OK;
+}
+
+static int fetch_obs(ljmd_ctx *c, double *dst, int per_rep, const int *idx)
+{
+    LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_obs, c->fw.obs, sizeof(double) * 4 * c->R,
+                                    cudaMemcpyDeviceToHost, c->stream));
+    LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (dst)
+        for (int r = 0; r < c->R; ++r)
+            for (int k = 0; k < per_rep; ++k) dst[(size_t)r * per_rep + k] = c->h_obs[4 * r + idx[k]];
+    return LJMD_OK;
+}
+
+} // namespace ljmd
+
+using namespace ljmd;
+
+// ==========================================================================================
+// Library / diagnostics
+// ==========================================================================================
+extern "C" int ljmd_version(void) { return LJMD_VERSION; }
+extern "C" const char *ljmd_last_error(void) { return g_err; }
+extern "C" int ljmd_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ==========================================================================================
+// init_params + compute_derived_params, base/md_types.f90:105-169
+// ==========================================================================================
+extern "C" int ljmd_params_init(ljmd_params *p, int32_t n, double box_length, double dt,
+                                double rc, int32_t num_cells)
+{
+    clear_error();
+    if (!p) return set_error(LJMD_ERR_NULL, "ljmd_params_init(): params is NULL.");
+    memset(p, 0, sizeof(*p));
+    p->n = n;
+    p->box_length = box_length;
+    p->dt = dt;
+    p->rc = rc;
+    p->num_cells = num_cells;
+    if (p->box_length > 0.0) {
+        p->inv_box_length = 1.0 / p->box_length;                     // :137
+        volatile double l2 = p->box_length * p->box_length;
+        p->volume = l2 * p->box_length;                              // :138  L**3
+        if (p->n > 0) p->density = (double)p->n / p->volume;         // :141
+    } else {
+        return set_error(LJMD_ERR_BOX, "compute_derived_params(): box_length must be > 0.");
+    }
+    if (p->rc > 0.0) {
+        p->rc_square = p->rc * p->rc;                                // :148
+    } else {
+        return set_error(LJMD_ERR_RC, "compute_derived_params(): rc (cutoff_radius) must be > 0.");
+    }
+    if (p->rc >= 0.5 * p->box_length)                                // :152
+        return set_error(LJMD_ERR_RC_HALF_BOX,
+                         "compute_derived_params(): rc (cutoff_radius) must be < L/2 (minimum image convention).");
+    if (p->dt > 0.0) {
+        p->dt_half = 0.5 * p->dt;                                    // :158
+        p->dt_square_half = p->dt_half * p->dt;                      // :159
+    } else {
+        return set_error(LJMD_ERR_DT, "compute_derived_params(): dt must be > 0.");
+    }
+    if (p->length_scale > 0.0) p->inv_length_scale = 1.0 / p->length_scale;
+    return LJMD_OK;
+}
+
+// ==========================================================================================
+// Contexts
+// ==========================================================================================
+extern "C" int ljmd_ctx_destroy(ljmd_ctx *c)
+{
+    if (!c) return LJMD_OK;
+    DeviceGuard g;
+    g.enter(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    drop_graphs(c);
+    cellwork_free(c);
+    cudaFree(c->state_block);
+    cudaFree(c->pw.fpart);
+    cudaFree(c->pw.spart);
+    cudaFree(c->fw.kpart);
+    cudaFree(c->fw.counter);
+    cudaFree(c->fw.ctl);
+    cudaFree(c->fw.pair_counts);
+    cudaFree(c->d_series);
+    if (c->h_obs) cudaFreeHost(c->h_obs);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_s0) cudaEventDestroy(c->ev_s0);
+    if (c->ev_s1) cudaEventDestroy(c->ev_s1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
+    delete c;
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_ctx_create(const ljmd_params *params, const ljmd_options *opts,
+                               ljmd_ctx **out)
+{
+    clear_error();
+    if (!out) return set_error(LJMD_ERR_NULL, "ljmd_ctx_create(): out is NULL.");
+    *out = nullptr;
+    LJMD_TRY(check_params(params, "ljmd_ctx_create"));
+    ljmd_options o = {LJMD_METHOD_AUTO, -1, 1, 0};
+    if (opts) o = *opts;
+    if (o.nreplicas < 1) return set_error(LJMD_ERR_ARG, "ljmd_ctx_create(): nreplicas must be >= 1.");
+    if (o.method < LJMD_METHOD_AUTO || o.method > LJMD_METHOD_CELLS)
+        return set_error(LJMD_ERR_ARG, "ljmd_ctx_create(): unknown method %d.", o.method);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_error(LJMD_ERR_CUDA, "ljmd_ctx_create(): no CUDA device available (this library has no CPU fallback).");
+    }
+    int dev = o.device;
+    if (dev < 0) LJMD_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= ndev) return set_error(LJMD_ERR_ARG, "ljmd_ctx_create(): device %d out of range.", dev);
+
+    ljmd_ctx *c = new (std::nothrow) ljmd_ctx();
+    if (!c) return set_error(LJMD_ERR_NOMEM, "ljmd_ctx_create(): out of host memory.");
+    memset(c, 0, sizeof(*c));
+    c->p = *params;
+    c->o = o;
+    c->device = dev;
+    c->R = o.nreplicas;
+    c->nR = (size_t)params->n * c->R;
+
+    const int nc = cells_per_edge_host(*params);
+    int method = o.method;
+    if (method == LJMD_METHOD_AUTO)
+        method = (nc >= 4 && params->n >= 16384) ? LJMD_METHOD_CELLS : LJMD_METHOD_ALLPAIRS;
+    if (method == LJMD_METHOD_CELLS && nc < 3) {
+        delete c;
+        return set_error(LJMD_ERR_UNSUPPORTED,
+                         "ljmd_ctx_create(): cell list needs floor(L/rc) >= 3 (got %d).", nc);
+    }
+    c->method = method;
+
+#define CREATE_CHECK(expr)                                                                  \
+    do {                                                                                    \
+        cudaError_t err__ = (expr);                                                         \
+        if (err__ != cudaSuccess) {                                                         \
+            int rc__ = set_error(LJMD_ERR_CUDA, "%s failed: %s", #expr,                     \
+                                 cudaGetErrorString(err__));                                \
+            ljmd_ctx_destroy(c);                                                            \
+            return rc__;                                                                    \
+        }                                                                                   \
+    } while (0)
+#define CREATE_TRY(expr)                                                                    \
+    do {                                                                                    \
+        int rc__ = (expr);                                                                  \
+        if (rc__ != LJMD_OK) { ljmd_ctx_destroy(c); return rc__; }                          \
+    } while (0)
+
+    DeviceGuard g;
+    CREATE_TRY(g.enter(dev));
+    CREATE_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CREATE_CHECK(cudaEventCreate(&c->ev0));
+    CREATE_CHECK(cudaEventCreate(&c->ev1));
+    CREATE_CHECK(cudaEventCreate(&c->ev_s0));
+    CREATE_CHECK(cudaEventCreate(&c->ev_s1));
+    refresh_constants(c);
+
+    // state block: 9 arrays | obs[R][4] | (ru: 3 arrays)
+    const bool track = (o.flags & LJMD_FLAG_TRACK_UNWRAPPED) != 0;
+    const size_t ndoubles = 9 * c->nR + 4 * (size_t)c->R + (track ? 3 * c->nR : 0);
+    CREATE_CHECK(cudaMalloc(&c->state_block, sizeof(double) * ndoubles));
+    CREATE_CHECK(cudaMemsetAsync(c->state_block, 0, sizeof(double) * ndoubles, c->stream)); // zero_state, md_types.f90:222-230
+    double *b = c->state_block;
+    c->st.rx = b + 0 * c->nR; c->st.ry = b + 1 * c->nR; c->st.rz = b + 2 * c->nR;
+    c->st.vx = b + 3 * c->nR; c->st.vy = b + 4 * c->nR; c->st.vz = b + 5 * c->nR;
+    c->st.ax = b + 6 * c->nR; c->st.ay = b + 7 * c->nR; c->st.az = b + 8 * c->nR;
+    c->fw.obs = b + 9 * c->nR;
+    if (track) {
+        double *u = b + 9 * c->nR + 4 * (size_t)c->R;
+        c->st.rux = u; c->st.ruy = u + c->nR; c->st.ruz = u + 2 * c->nR;
+    }
+
+    c->fw.block = 256;
+    c->fw.nblk = (params->n + c->fw.block - 1) / c->fw.block;
+    CREATE_CHECK(cudaMalloc(&c->fw.kpart, sizeof(double) * 3 * (size_t)c->fw.nblk * c->R));
+    CREATE_CHECK(cudaMalloc(&c->fw.counter, sizeof(unsigned) * (c->R + 1)));
+    CREATE_CHECK(cudaMemsetAsync(c->fw.counter, 0, sizeof(unsigned) * (c->R + 1), c->stream));
+    CREATE_CHECK(cudaMalloc(&c->fw.ctl, sizeof(StepCtl)));
+    CREATE_CHECK(cudaMemsetAsync(c->fw.ctl, 0, sizeof(StepCtl), c->stream));
+    CREATE_CHECK(cudaMallocHost(&c->h_obs, sizeof(double) * 4 * (size_t)c->R + 64));
+
+    if (method == LJMD_METHOD_CELLS) CREATE_TRY(cellwork_plan(c));
+    else CREATE_TRY(pairwork_plan(c));
+    CREATE_CHECK(cudaStreamSynchronize(c->stream));
+#undef CREATE_CHECK
+#undef CREATE_TRY
+    *out = c;
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_ctx_upload(ljmd_ctx *c, const double *rx, const double *ry, const double *rz,
+                               const double *vx, const double *vy, const double *vz,
+                               const double *ax, const double *ay, const double *az)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_upload(): ctx is NULL.");
+    DeviceGuard g;
+    LJMD_TRY(g.enter(c->device));
+    LJMD_TRY(ensure_stage(c));
+    const double *src[9] = {rx, ry, rz, vx, vy, vz, ax, ay, az};
+    const size_t bytes = sizeof(double) * c->nR;
+    // pack contiguous runs of non-NULL arrays into the pinned stage, one H2D per run
+    int k = 0;
+    while (k < 9) {
+        if (!src[k]) { ++k; continue; }
+        int e = k;
+        while (e < 9 && src[e]) { memcpy(c->h_stage + (size_t)e * c->nR, src[e], bytes); ++e; }
+        LJMD_CUDA_CHECK(cudaMemcpyAsync(c->state_block + (size_t)k * c->nR,
+                                        c->h_stage + (size_t)k * c->nR, bytes * (e - k),
+                                        cudaMemcpyHostToDevice, c->stream));
+        k = e;
+    }
+    if (c->st.rux && (rx || ry || rz)) { // ru(t=0) = r(t=0), md_simulation_program.f90:229-231
+        LJMD_CUDA_CHECK(cudaMemcpyAsync(c->st.rux, c->st.rx, 3 * bytes, cudaMemcpyDeviceToDevice,
+                                        c->stream));
+    }
+    LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_ctx_download(ljmd_ctx *c, double *rx, double *ry, double *rz, double *vx,
+                                 double *vy, double *vz, double *ax, double *ay, double *az)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_download(): ctx is NULL.");
+    DeviceGuard g;
+    LJMD_TRY(g.enter(c->device));
+    LJMD_TRY(ensure_stage(c));
+    double *dst[9] = {rx, ry, rz, vx, vy, vz, ax, ay, az};
+    const size_t bytes = sizeof(double) * c->nR;
+    int k = 0;
+    while (k < 9) {
+        if (!dst[k]) { ++k; continue; }
+        int e = k;
+        while (e < 9 && dst[e]) ++e;
+        LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_stage + (size_t)k * c->nR,
+                                        c->state_block + (size_t)k * c->nR, bytes * (e - k),
+                                        cudaMemcpyDeviceToHost, c->stream));
+        k = e;
+    }
+    LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (k = 0; k < 9; ++k)
+        if (dst[k]) memcpy(dst[k], c->h_stage + (size_t)k * c->nR, bytes);
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_ctx_download_unwrapped(ljmd_ctx *c, double *rux, double *ruy, double *ruz)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_download_unwrapped(): ctx is NULL.");
+    if (!c->st.rux)
+        return set_error(LJMD_ERR_ARG, "ljmd_ctx_download_unwrapped(): context was created without LJMD_FLAG_TRACK_UNWRAPPED.");
+    DeviceGuard g;
+    LJMD_TRY(g.enter(c->device));
+    const size_t bytes = sizeof(double) * c->nR;
+    double *dst[3] = {rux, ruy, ruz};
+    double *srcs[3] = {c->st.rux, c->st.ruy, c->st.ruz};
+    for (int k = 0; k < 3; ++k)
+        if (dst[k]) LJMD_CUDA_CHECK(cudaMemcpyAsync(dst[k], srcs[k], bytes, cudaMemcpyDeviceToHost, c->stream));
+    LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_ctx_compute_forces(ljmd_ctx *c, double *obs3)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_compute_forces(): ctx is NULL.");
+    DeviceGuard g;
+    LJMD_TRY(g.enter(c->device));
+    LJMD_TRY(enqueue_force(c));
+    LJMD_TRY(launch_finalize(c, false));
+    const int idx[3] = {0, 2, 3};
+    return fetch_obs(c, obs3, 3, idx);
+}
+
+extern "C" int ljmd_ctx_step(ljmd_ctx *c, int32_t nsteps, double *obs4)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_step(): ctx is NULL.");
+    if (nsteps < 0) return set_error(LJMD_ERR_ARG, "ljmd_ctx_step(): nsteps must be >= 0.");
+    DeviceGuard g;
+    LJMD_TRY(g.enter(c->device));
+    LJMD_CUDA_CHECK(cudaEventRecord(c->ev_s0, c->stream));
+    LJMD_TRY(run_steps(c, nsteps));
+    LJMD_CUDA_CHECK(cudaEventRecord(c->ev_s1, c->stream));
+    const int idx[4] = {0, 1, 2, 3};
+    LJMD_TRY(fetch_obs(c, obs4, 4, idx));
+    float ms = 0.f;
+    LJMD_CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev_s0, c->ev_s1));
+    c->last_step_ms = ms;
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_ctx_step_series(ljmd_ctx *c, int32_t nsteps, double *series)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_step_series(): ctx is NULL.");
+    if (nsteps < 0) return set_error(LJMD_ERR_ARG, "ljmd_ctx_step_series(): nsteps must be >= 0.");
+    if (!series) return set_error(LJMD_ERR_NULL, "ljmd_ctx_step_series(): series is NULL.");
+    if (nsteps == 0) return LJMD_OK;
+    DeviceGuard g;
+    LJMD_TRY(g.enter(c->device));
+    if (c->series_cap < nsteps) {
+        cudaFree(c->d_series);
+        c->d_series = nullptr;
+        c->series_cap = 0;
+        LJMD_CUDA_CHECK(cudaMalloc(&c->d_series, sizeof(double) * 4 * (size_t)c->R * nsteps));
+        c->series_cap = nsteps;
+    }
+    LJMD_TRY(set_ctl(c, nsteps, c->d_series));
+    int rc = run_steps(c, nsteps);
+    if (rc == LJMD_OK) {
+        cudaError_t e = cudaMemcpyAsync(series, c->d_series, sizeof(double) * 4 * (size_t)c->R * nsteps,
+                                        cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = set_error(LJMD_ERR_CUDA, "series download failed: %s", cudaGetErrorString(e));
+    }
+    int rc2 = set_ctl(c, 0, nullptr);
+    return rc != LJMD_OK ? rc : rc2;
+}
+
+extern "C" int ljmd_ctx_kinetic_energy(ljmd_ctx *c, double *ekin)
+{
+    clear_error();
+    if (!c || !ekin) return set_error(LJMD_ERR_NULL, "ljmd_ctx_kinetic_energy(): NULL argument.");
+    DeviceGuard g;
+    LJMD_TRY(g.enter(c->device));
+    // reuse kpart as scratch output (R doubles fit: nblk*3*R >= R)
+    LJMD_TRY(launch_ekin_driver(c, c->fw.kpart));
+    LJMD_CUDA_CHECK(cudaMemcpyAsync(ekin, c->fw.kpart, sizeof(double) * c->R, cudaMemcpyDeviceToHost, c->stream));
+    LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_ctx_last_step_ms(const ljmd_ctx *c, double *ms)
+{
+    if (!c || !ms) return set_error(LJMD_ERR_NULL, "ljmd_ctx_last_step_ms(): NULL argument.");
+    *ms = c->last_step_ms;
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_ctx_method(const ljmd_ctx *c) { return c ? c->method : -1; }
+extern "C" int ljmd_ctx_cells_per_edge(const ljmd_ctx *c) { return c ? c->cw.nc : 0; }
+extern "C" int64_t ljmd_ctx_launch_count(const ljmd_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int ljmd_ctx_force_timing(ljmd_ctx *c, int32_t enable, double *ms_total, int64_t *n_evals)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_force_timing(): ctx is NULL.");
+    if (ms_total) *ms_total = c->force_ms;
+    if (n_evals) *n_evals = c->force_evals;
+    c->timing = enable != 0;
+    c->force_ms = 0.0;
+    c->force_evals = 0;
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_ctx_pair_counts(ljmd_ctx *c, int64_t *n_candidates, int64_t *n_in_cutoff)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_pair_counts(): ctx is NULL.");
+    DeviceGuard g;
+    LJMD_TRY(g.enter(c->device));
+    if (!c->fw.pair_counts) LJMD_CUDA_CHECK(cudaMalloc(&c->fw.pair_counts, 2 * sizeof(unsigned long long) * c->R));
+    LJMD_CUDA_CHECK(cudaMemsetAsync(c->fw.pair_counts, 0, 2 * sizeof(unsigned long long) * c->R, c->stream));
+    int rc = enqueue_force(c); // positions unchanged: recomputes the same partials, plus counts
+    unsigned long long h[2] = {0, 0};
+    if (rc == LJMD_OK) {
+        cudaError_t e = cudaMemcpyAsync(h, c->fw.pair_counts, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = set_error(LJMD_ERR_CUDA, "pair count download failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(c->fw.pair_counts);
+    c->fw.pair_counts = nullptr;
+    if (rc != LJMD_OK) return rc;
+    if (c->method == LJMD_METHOD_ALLPAIRS) {
+        const int64_t n = c->p.n;
+        if (n_candidates) *n_candidates = n * (n - 1) / 2 * c->R;
+        // the full-matrix kernel counts ordered pairs
+        if (n_in_cutoff) *n_in_cutoff = (int64_t)(c->pw.variant == 0 ? h[1] / 2 : h[1]);
+    } else {
+        if (n_candidates) *n_candidates = (int64_t)h[0];
+        if (n_in_cutoff) *n_in_cutoff = (int64_t)h[1];
+    }
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_measure_fp64_peak(int32_t device, double *tflops)
+{
+    clear_error();
+    if (!tflops) return set_error(LJMD_ERR_NULL, "ljmd_measure_fp64_peak(): tflops is NULL.");
+    if (ljmd_device_count() == 0)
+        return set_error(LJMD_ERR_CUDA, "ljmd_measure_fp64_peak(): no CUDA device available.");
+    return measure_fp64_peak(device, tflops);
+}
+
+// ==========================================================================================
+// Stateless drop-in pair.  A cached context keeps the device buffers between calls.
+// ==========================================================================================
+namespace {
+std::mutex g_compat_mu;
+ljmd_ctx *g_compat = nullptr;
+
+int compat_ctx(const ljmd_params *p, const char *who, ljmd_ctx **out)
+{
+    LJMD_TRY(check_params(p, who));
+    if (g_compat && (g_compat->p.n != p->n)) { ljmd_ctx_destroy(g_compat); g_compat = nullptr; }
+    if (g_compat && g_compat->method == LJMD_METHOD_CELLS && cells_per_edge_host(*p) != g_compat->cw.nc) {
+        ljmd_ctx_destroy(g_compat); g_compat = nullptr;
+    }
+    if (!g_compat) {
+        ljmd_options o = {LJMD_METHOD_AUTO, -1, 1, 0};
+        LJMD_TRY(ljmd_ctx_create(p, &o, &g_compat));
+    } else if (memcmp(&g_compat->p, p, sizeof(*p)) != 0) {
+        g_compat->p = *p;
+        refresh_constants(g_compat);
+        drop_graphs(g_compat);
+    }
+    *out = g_compat;
+    return LJMD_OK;
+}
+} // namespace
+
+extern "C" int ljmd_compat_release(void)
+{
+    std::lock_guard<std::mutex> lk(g_compat_mu);
+    if (g_compat) { ljmd_ctx_destroy(g_compat); g_compat = nullptr; }
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_compute_lj(const ljmd_params *params, const double *rx, const double *ry,
+                               const double *rz, double *ax, double *ay, double *az,
+                               double *epot, double *d_epot, double *dd_epot)
+{
+    clear_error();
+    std::lock_guard<std::mutex> lk(g_compat_mu);
+    LJMD_TRY(check_params(params, "compute_lj_potential_energy"));
+    if (!rx || !ry || !rz || !ax || !ay || !az)
+        return set_error(LJMD_ERR_NULL, "compute_lj_potential_energy(): state arrays are not allocated.");
+    if (!epot || !d_epot || !dd_epot)
+        return set_error(LJMD_ERR_NULL, "compute_lj_potential_energy(): output scalar is NULL.");
+    ljmd_ctx *c = nullptr;
+    LJMD_TRY(compat_ctx(params, "compute_lj_potential_energy", &c));
+    DeviceGuard g;
+    LJMD_TRY(g.enter(c->device));
+    LJMD_TRY(ensure_stage(c));
+    const size_t nb = sizeof(double) * c->nR;
+    memcpy(c->h_stage, rx, nb);
+    memcpy(c->h_stage + c->nR, ry, nb);
+    memcpy(c->h_stage + 2 * c->nR, rz, nb);
+    LJMD_CUDA_CHECK(cudaMemcpyAsync(c->st.rx, c->h_stage, 3 * nb, cudaMemcpyHostToDevice, c->stream));
+    LJMD_TRY(enqueue_force(c));
+    LJMD_TRY(launch_finalize(c, false));
+    // accelerations and obs are contiguous: ax ay az | obs
+    LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_stage + 6 * c->nR, c->st.ax, 3 * nb + sizeof(double) * 4,
+                                    cudaMemcpyDeviceToHost, c->stream));
+    LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    memcpy(ax, c->h_stage + 6 * c->nR, nb);
+    memcpy(ay, c->h_stage + 7 * c->nR, nb);
+    memcpy(az, c->h_stage + 8 * c->nR, nb);
+    const double *o = c->h_stage + 9 * c->nR;
+    *epot = o[0]; *d_epot = o[2]; *dd_epot = o[3];
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_verlet_step(const ljmd_params *params, double *rx, double *ry, double *rz,
+                                double *vx, double *vy, double *vz, double *ax, double *ay,
+                                double *az, double *epot, double *ekin, double *d_epot,
+                                double *dd_epot)
+{
+    clear_error();
+    std::lock_guard<std::mutex> lk(g_compat_mu);
+    if (params && params->n <= 0) return set_error(LJMD_ERR_N, "verlet_step(): params%%n must be > 0.");
+    if (!rx || !ry || !rz || !vx || !vy || !vz || !ax || !ay || !az)
+        return set_error(LJMD_ERR_NULL, "verlet_step(): state arrays are not allocated.");
+    if (!epot || !ekin || !d_epot || !dd_epot)
+        return set_error(LJMD_ERR_NULL, "verlet_step(): output scalar is NULL.");
+    ljmd_ctx *c = nullptr;
+    LJMD_TRY(compat_ctx(params, "verlet_step", &c));
+    DeviceGuard g;
+    LJMD_TRY(g.enter(c->device));
+    LJMD_TRY(ensure_stage(c));
+    const size_t nb = sizeof(double) * c->nR;
+    double *arr[9] = {rx, ry, rz, vx, vy, vz, ax, ay, az};
+    for (int k = 0; k < 9; ++k) memcpy(c->h_stage + (size_t)k * c->nR, arr[k], nb);
+    LJMD_CUDA_CHECK(cudaMemcpyAsync(c->state_block, c->h_stage, 9 * nb, cudaMemcpyHostToDevice, c->stream));
+    LJMD_TRY(enqueue_step(c));
+    LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_stage, c->state_block, 9 * nb + sizeof(double) * 4,
+                                    cudaMemcpyDeviceToHost, c->stream));
+    LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 9; ++k) memcpy(arr[k], c->h_stage + (size_t)k * c->nR, nb);
+    const double *o = c->h_stage + 9 * c->nR;
+    *epot = o[0]; *ekin = o[1]; *d_epot = o[2]; *dd_epot = o[3];
+    return LJMD_OK;
+}

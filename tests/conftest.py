@@ -1,0 +1,74 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def O():
+    """The CPU oracle (checker only)."""
+    from oracle import oracle_py
+
+    oracle_py.build()
+    return oracle_py
+
+
+@pytest.fixture(scope="session")
+def lj():
+    """The product package; the CUDA library must already be built (no fallback)."""
+    import __graft_entry__ as g
+
+    lib = os.path.join(g.PKG, "lib", "libljmd.so")
+    if not os.path.exists(lib):
+        g.build()
+    import ljmd_b200
+
+    ljmd_b200.load_library()
+    return ljmd_b200
+
+
+# ---- the benchmark / parity configurations of SURVEY.md section 8d ------------------------
+CONFIGS = {
+    # name: (k, L, rc, dt, E_target or None, T_target or None)
+    "cfg1": dict(k=5, L=10.0, rc=4.9, dt=1e-4, e_target=-555.0),
+    "cfg2": dict(k=10, L=20.0, rc=9.8, dt=1e-4, e_target=-4440.0),
+    "cfg3": dict(k=20, L=34.19951893353394, rc=2.5, dt=1e-3, t_target=1.0),
+    "small_cells": dict(k=6, L=10.259855680060184, rc=2.5, dt=1e-3, t_target=1.0),  # N=864, rho=0.8
+}
+
+
+def make_config(O, name, seed=-12345):
+    """Initial configuration as md_initial_config_program builds it (no warm-up)."""
+    c = CONFIGS[name]
+    n = 4 * c["k"] ** 3
+    p = O.params_init(n, c["L"], c["dt"], c["rc"], c["k"])
+    cells = O.cells_per_edge(p) >= 3 and n > 2000
+    st, _, _ = O.initial_config(p, seed, c.get("e_target", 0.0) or 0.0,
+                                c.get("t_target", 0.0) or 0.0, cells=cells)
+    return p, st
+
+
+def melt(O, p, st, nsteps, cells=False):
+    """Advance a copy of the state with the oracle to get a disordered configuration."""
+    s = [a.copy() for a in st]
+    for _ in range(nsteps):
+        O.verlet_step(p, s, cells=cells)
+    return s
+
+
+def rel_err(got, want):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    scale = np.max(np.abs(want))
+    if scale == 0.0:
+        return float(np.max(np.abs(got - want)))
+    return float(np.max(np.abs(got - want)) / scale)

@@ -1,0 +1,241 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+inputs.  Tolerance (north star): forces, U, virial terms within 1e-12 relative per step.
+Forces are compared relative to max|a| of the configuration; scalars relative to their value."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import make_config, melt, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _state(lj, arrs):
+    return lj.SimState.from_arrays([a.copy() for a in arrs])
+
+
+def _check_forces(lj, O, p_o, arrs, tol=TOL):
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    s = _state(lj, arrs)
+    e, d, dd = lj.compute_lj_potential_energy(p, s)
+    ax, ay, az, e0, d0, dd0 = O.compute_lj(p_o, *arrs[:3])
+    assert rel_err(s.ax, ax) <= tol and rel_err(s.ay, ay) <= tol and rel_err(s.az, az) <= tol
+    assert abs(e - e0) <= tol * abs(e0)
+    assert abs(d - d0) <= tol * abs(d0)
+    assert abs(dd - dd0) <= tol * abs(dd0)
+    return s
+
+
+def test_device_present(lj):
+    assert lj.device_count() >= 1
+
+
+def test_compute_lj_cfg1_melted(lj, O):
+    p, st = make_config(O, "cfg1")
+    s = melt(O, p, st, 200)
+    _check_forces(lj, O, p, s)
+
+
+def test_compute_lj_cfg1_fcc_t0(lj, O):
+    # perfect lattice: every a_i ~ 0 (cancellation); compare absolutely against the pair scale
+    p_o, st = make_config(O, "cfg1")
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    s = _state(lj, st)
+    e, d, dd = lj.compute_lj_potential_energy(p, s)
+    _, _, _, e0, d0, dd0 = O.compute_lj(p_o, *st[:3])
+    assert max(np.abs(s.ax).max(), np.abs(s.ay).max(), np.abs(s.az).max()) < 1e-12
+    assert abs(e - e0) <= TOL * abs(e0) and abs(d - d0) <= TOL * abs(d0) and abs(dd - dd0) <= TOL * abs(dd0)
+
+
+def test_golden_cfg1(lj):
+    g = np.load(os.path.join(GOLD, "cfg1_n500.npz"))
+    p = lj.init_params(500, 10.0, 1e-4, 4.9, 5)
+    s = _state(lj, g["state0"])
+    obs = lj.verlet_step(p, s)
+    for got, want in zip(obs, g["obs1"]):
+        assert abs(got - want) <= TOL * abs(want)
+    for k, name in enumerate(lj.SimState.NAMES):
+        assert rel_err(getattr(s, name), g["state1"][k]) <= TOL, name
+    s = _state(lj, g["state200"])
+    e, d, dd = lj.compute_lj_potential_energy(p, s)
+    for got, want in zip((e, d, dd), g["obs_f200"]):
+        assert abs(got - want) <= TOL * abs(want)
+
+
+def test_verlet_step_cfg2(lj, O):
+    p_o, st = make_config(O, "cfg2")
+    s0 = melt(O, p_o, st, 3)
+    ref = [a.copy() for a in s0]
+    ref_obs = O.verlet_step(p_o, ref)
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    s = _state(lj, s0)
+    obs = lj.verlet_step(p, s)
+    for got, want in zip(obs, ref_obs):
+        assert abs(got - want) <= TOL * abs(want)
+    for name, want in zip(lj.SimState.NAMES, ref):
+        assert rel_err(getattr(s, name), want) <= TOL, name
+    # positions and half-kicked velocities use the reference's exact operation order
+    assert np.array_equal(s.rx, ref[0]) and np.array_equal(s.ry, ref[1]) and np.array_equal(s.rz, ref[2])
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 127, 128, 129, 500, 1000, 1537])
+def test_ragged_sizes_random_positions(lj, O, n):
+    rng = np.random.default_rng(1234 + n)
+    L = 12.0
+    p = O.params_init(n, L, 1e-3, 3.0, 0)
+    # random gas, but keep pairs apart so r^-12 stays finite: jittered grid
+    m = int(np.ceil(n ** (1 / 3)))
+    g = np.stack(np.meshgrid(*[np.arange(m)] * 3, indexing="ij"), -1).reshape(-1, 3)[:n]
+    pos = (g + 0.5 + 0.3 * (rng.random((n, 3)) - 0.5)) * (L / m)
+    arrs = [np.ascontiguousarray(pos[:, k]) for k in range(3)] + [np.zeros(n) for _ in range(6)]
+    _check_forces(lj, O, p, arrs)
+    assert True
+
+
+def test_unwrapped_inputs_match(lj, O):
+    """The force routine is specified for unwrapped inputs too (geometry_pbc.f90:18-19)."""
+    p, st = make_config(O, "cfg1")
+    s = melt(O, p, st, 100)
+    rng = np.random.default_rng(7)
+    for k in range(3):
+        s[k] = s[k] + p.box_length * rng.integers(-2, 3, size=p.n)
+    _check_forces(lj, O, p, s, tol=1e-11)
+
+
+def test_pair_counts_match(lj, O):
+    p_o, st = make_config(O, "cfg1")
+    s = melt(O, p_o, st, 200)
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    with lj.Context(p, method=lj.METHOD_ALLPAIRS) as ctx:
+        ctx.upload(_state(lj, s))
+        cand, cut = ctx.pair_counts()
+    assert cand == 500 * 499 // 2
+    assert cut == O.count_pairs_in_cutoff(p_o, *s[:3])
+
+
+def test_newton3_exact_cancellation(lj, O):
+    p_o, st = make_config(O, "cfg2")
+    s0 = melt(O, p_o, st, 2)
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    s = _state(lj, s0)
+    lj.compute_lj_potential_energy(p, s)
+    scale = np.abs(s.ax).max()
+    assert abs(s.ax.sum()) < 1e-10 * scale * np.sqrt(p.n)
+
+
+def test_run_to_run_determinism(lj, O):
+    p_o, st = make_config(O, "cfg1")
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    outs = []
+    for _ in range(3):
+        with lj.Context(p, method=lj.METHOD_ALLPAIRS) as ctx:
+            ctx.upload(_state(lj, st))
+            ctx.compute_forces()
+            obs = ctx.step(200)
+            d = ctx.download()
+            outs.append((obs.copy(), [a.copy() for a in d.arrays()]))
+    for o, arrs in outs[1:]:
+        assert np.array_equal(o, outs[0][0])
+        for a, b in zip(arrs, outs[0][1]):
+            assert np.array_equal(a, b)  # bitwise
+
+
+def test_resident_multistep_vs_oracle(lj, O):
+    p_o, st = make_config(O, "cfg1")
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    nsteps = 100
+    ref = [a.copy() for a in st]
+    _, ref_ser = O.run_steps(p_o, nsteps, ref, want_series=True)
+    with lj.Context(p, method=lj.METHOD_ALLPAIRS) as ctx:
+        ctx.upload(_state(lj, st))
+        ser = ctx.step_series(nsteps)
+        d = ctx.download()
+    # first step within 1e-12; afterwards round-off differences grow (chaotic dynamics)
+    assert np.all(np.abs(ser[0] - ref_ser[0]) <= TOL * np.abs(ref_ser[0]))
+    assert np.all(np.abs(ser - ref_ser) <= 1e-9 * np.abs(ref_ser))
+    assert rel_err(d.rx, ref[0]) < 1e-9
+
+
+def test_graph_path_equals_single_steps(lj, O):
+    p_o, st = make_config(O, "cfg1")
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    with lj.Context(p, method=lj.METHOD_ALLPAIRS) as a, lj.Context(p, method=lj.METHOD_ALLPAIRS) as b:
+        a.upload(_state(lj, st)); b.upload(_state(lj, st))
+        oa = a.step(70)                      # graph chunks + remainder
+        for _ in range(70):
+            ob = b.step(1)                   # direct launches
+        assert np.array_equal(oa, ob)
+        da, db = a.download(), b.download()
+        for x, y in zip(da.arrays(), db.arrays()):
+            assert np.array_equal(x, y)
+        assert a.launch_count == b.launch_count == 70 * 3
+
+
+def test_unwrapped_tracking(lj, O):
+    p_o, st = make_config(O, "cfg1")
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    # speed the particles up so that some cross the box boundary
+    fast = [a.copy() for a in st]
+    for k in (3, 4, 5):
+        fast[k] *= 30.0
+    p_fast = O.params_init(500, 10.0, 1e-3, 4.9, 5)
+    ref = [a.copy() for a in fast]
+    ru = [a.copy() for a in ref[:3]]
+    O.run_steps(p_fast, 60, ref, ru=ru)
+    pf = lj.SimParams.from_buffer_copy(bytes(p_fast))
+    with lj.Context(pf, method=lj.METHOD_ALLPAIRS, flags=lj.FLAG_TRACK_UNWRAPPED) as ctx:
+        ctx.upload(_state(lj, fast))
+        ctx.step(60)
+        got = ctx.download_unwrapped()
+        d = ctx.download()
+    assert np.abs(np.array(ru) - np.array(ref[:3])).max() > 1.0  # something actually crossed
+    for a, b in zip(got, ru):
+        assert np.abs(a - b).max() < 1e-8
+    assert rel_err(d.rx, ref[0]) < 1e-8
+
+
+def test_replicas_are_independent(lj, O):
+    p_o, st = make_config(O, "cfg1")
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    R = 3
+    states = []
+    for r in range(R):
+        s_r, _, _ = O.initial_config(p_o, -(12345 + r), -555.0)
+        states.append(s_r)
+    batched = [np.ascontiguousarray(np.stack([states[r][k] for r in range(R)])) for k in range(9)]
+    with lj.Context(p, method=lj.METHOD_ALLPAIRS, nreplicas=R) as ctx:
+        ctx.upload(lj.SimState.from_arrays(batched))
+        obs = ctx.step(20)
+        d = ctx.download()
+    for r in range(R):
+        ref = [a.copy() for a in states[r]]
+        ro = O.run_steps(p_o, 20, ref)
+        assert np.all(np.abs(obs[r] - ro) <= 1e-10 * np.abs(ro))
+        assert rel_err(d.rx[r], ref[0]) < 1e-10
+
+
+def test_kinetic_energy_driver_order(lj, O):
+    p_o, st = make_config(O, "cfg1")
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    with lj.Context(p, method=lj.METHOD_ALLPAIRS) as ctx:
+        ctx.upload(_state(lj, st))
+        k = ctx.kinetic_energy()
+    k0 = O.ekin_driver(*st[3:6])
+    assert abs(k - k0) <= TOL * k0
+
+
+def test_error_paths_on_gpu(lj):
+    p = lj.init_params(500, 10.0, 1e-4, 4.9, 5)
+    with pytest.raises(lj.LjmdError) as e:
+        lj.Context(p, method=lj.METHOD_CELLS)   # floor(L/rc) = 2 < 3
+    assert e.value.code == 10
+    with pytest.raises(lj.LjmdError):
+        lj.Context(p, nreplicas=0)
+
+
+def test_fp64_peak_measurement(lj):
+    tf = lj.measure_fp64_peak()
+    assert 10.0 < tf < 60.0, tf

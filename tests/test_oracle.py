@@ -1,0 +1,168 @@
+"""CPU tests of the oracle (oracle/ljmd_oracle.c) against analytic identities, the exactly
+reproducible RNG stream, the SURVEY.md Appendix-B anchors and the committed golden fixtures.
+
+PARITY UNPINNED: the reference has no tests/golden vectors and no Fortran compiler exists here,
+so none of this compares with output of the reference's own build.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import make_config, melt, rel_err
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_params_layout_and_derived(O):
+    import ctypes
+
+    assert ctypes.sizeof(O.OrcParams) == 96  # md_types.f90:27-50 as gfortran lays it out
+    p = O.params_init(500, 10.0, 1e-4, 4.9, 5)
+    assert p.inv_box_length == 1.0 / 10.0
+    assert p.volume == 1000.0 and p.density == 0.5
+    assert p.rc_square == 4.9 * 4.9
+    assert p.dt_half == 0.5e-4 and p.dt_square_half == 0.5e-4 * 1e-4
+
+
+@pytest.mark.parametrize("args,code", [
+    ((500, 0.0, 1e-4, 4.9), 2), ((500, 10.0, 1e-4, 0.0), 4), ((500, 10.0, 1e-4, 5.0), 7),
+    ((500, 10.0, 0.0, 4.9), 8),
+])
+def test_params_guards(O, args, code):
+    with pytest.raises(O.OracleError) as e:
+        O.params_init(*args)
+    assert e.value.code == code
+
+
+def test_rng_stream_exact(O):
+    # all values are integers < 4e6 scaled by 2.5e-7 => exact
+    g = O.Rng(-12345)
+    d = [g.uniform() for _ in range(1500)]
+    expect = [0.6283575, 0.81823825, 0.169642, 0.19663425, 0.9045145, 0.60583975]
+    for a, b in zip(d[:6], expect):
+        assert abs(a - b) < 1e-15
+        assert abs(a / 2.5e-7 - round(a / 2.5e-7)) < 1e-6
+    assert abs(sum(d) - 741.57097625) < 1e-9
+    assert all(0.0 <= x < 1.0 for x in d)
+
+
+def test_minimum_image_examples(O):
+    # geometry_pbc.f90:70-74 worked example and ties (dnint rounds half away from zero)
+    assert abs(O.minimum_image(9.5, 10.0, 0.1) - (-0.5)) < 1e-15
+    assert O.minimum_image(5.0, 10.0, 0.1) == -5.0   # dnint(0.5) = 1
+    assert O.minimum_image(-5.0, 10.0, 0.1) == 5.0   # dnint(-0.5) = -1
+    assert O.minimum_image(0.3, 10.0, 0.1) == 0.3
+
+
+def test_wrap_examples(O):
+    # geometry_pbc.f90:33-37
+    rx = np.array([9.8, 10.2, -0.4, 20.7, -1e-17])
+    ry, rz = rx.copy(), rx.copy()
+    O.wrap_positions(rx, ry, rz, 10.0)
+    assert np.allclose(rx[:4], [9.8, 0.2, 9.6, 0.7], atol=1e-14)
+    assert rx[4] == 10.0  # tiny negative wraps to exactly L
+    assert np.all(ry == rx) and np.all(rz == rx)
+
+
+def test_tail_constants_analytic(O):
+    p = O.params_init(500, 10.0, 1e-4, 4.9, 5)
+    tu, td, tdd = O.tail_corrections(p)
+    rho, rc, n = 0.5, 4.9, 500
+    # standard LJ tails: U = (8/3) pi N rho [1/(3 rc^9) - 1/rc^3]
+    u_an = (8.0 / 3.0) * np.pi * n * rho * (1.0 / (3 * rc ** 9) - 1.0 / rc ** 3)
+    assert abs(tu - u_an) < 1e-12 * abs(u_an)
+    assert abs(tu - (-17.80163591736684)) < 1e-10
+    assert abs(td - 106.80724319074815) < 1e-9
+    assert abs(tdd - (-747.6198345738022)) < 1e-9
+
+
+def test_cfg1_anchors(O):
+    p, st = make_config(O, "cfg1")
+    ax, ay, az, e, d, dd = O.compute_lj(p, *st[:3])
+    assert O.count_pairs_in_cutoff(p, *st[:3]) == 62000
+    assert abs(e - (-1617.29012097504)) < 1e-8
+    assert abs(d - 8566.376918596876) < 1e-7
+    assert abs(dd - (-46316.27274313783)) < 1e-6
+    assert max(np.abs(ax).max(), np.abs(ay).max(), np.abs(az).max()) < 1e-13  # perfect FCC
+    k = O.ekin_driver(*st[3:6])
+    assert abs(k - 1062.29012097504) < 1e-8
+    assert abs((e + k) - (-555.0)) < 1e-10
+    s = [a.copy() for a in st]
+    o1 = O.run_steps(p, 1, s)
+    assert abs(o1[0] - (-1617.2902880702816)) < 1e-8 and abs(o1[1] - 1062.290288070596) < 1e-8
+    o10 = O.run_steps(p, 9, s)
+    assert abs(o10[0] - (-1616.8239881221884)) < 1e-7
+    assert abs(o10[0] + o10[1] - (-554.516553827825)) < 1e-7
+
+
+def test_newton3_and_momentum(O):
+    p, st = make_config(O, "cfg1")
+    s = melt(O, p, st, 200)
+    ax, ay, az, *_ = O.compute_lj(p, *s[:3])
+    scale = np.abs(ax).max()
+    assert abs(ax.sum()) < 1e-10 * scale and abs(ay.sum()) < 1e-10 * scale
+    assert abs(s[3].sum()) < 1e-9 and abs(s[4].sum()) < 1e-9  # COM velocity stays ~0
+
+
+def test_energy_conservation_smooth_case(O):
+    # NVE: the potential is truncated, not shifted (lj_potential_energy.f90:132-140), so every
+    # cutoff crossing jumps E by |U(rc)| = 0.016; the total stays within 1 % over 300 steps
+    p, st = make_config(O, "small_cells")
+    s = [a.copy() for a in st]
+    _, ser = O.run_steps(p, 300, s, want_series=True)
+    etot = ser[:, 0] + ser[:, 1]
+    assert np.ptp(etot) < 1e-2 * abs(etot[0])
+
+
+def test_golden_cfg1(O):
+    g = np.load(os.path.join(GOLD, "cfg1_n500.npz"))
+    p, st = make_config(O, "cfg1")
+    assert np.array_equal(np.array(st), g["state0"])  # bit-exact regression
+    s = [a.copy() for a in st]
+    o1 = O.run_steps(p, 1, s)
+    assert np.array_equal(np.array(s), g["state1"]) and np.array_equal(o1, g["obs1"])
+    o10 = O.run_steps(p, 9, s)
+    assert np.array_equal(o10, g["obs10"])
+    assert int(g["pairs_in_cutoff_t0"]) == 62000
+
+
+def test_cell_oracle_matches_allpairs(O):
+    g = np.load(os.path.join(GOLD, "cells_n864.npz"))
+    p = O.params_init(864, float(g["L"]), 1e-3, 2.5, 6)
+    s = [np.ascontiguousarray(a) for a in g["state300"]]
+    a = O.compute_lj(p, *s[:3])
+    b = O.compute_lj_cells(p, *s[:3])
+    for k in range(3):
+        assert rel_err(b[k], a[k]) < 1e-13
+    for k in range(3, 6):
+        assert abs(a[k] - b[k]) <= 1e-13 * abs(a[k])
+    assert b[7] == O.count_pairs_in_cutoff(p, *s[:3]) == int(g["n_cut"])
+    cell = O.cell_assign(p, *s[:3])
+    start, order = O.cell_sort(p, cell)
+    assert np.array_equal(cell, g["cell"]) and np.array_equal(order, g["order"])
+    assert start[-1] == 864 and np.all(np.diff(start) >= 0)
+    assert np.all(np.diff(cell[order]) >= 0)  # sorted by cell
+    for c in range(len(start) - 1):           # stable: ascending original index within a cell
+        seg = order[start[c]:start[c + 1]]
+        assert np.all(np.diff(seg) > 0)
+
+
+def test_cell_oracle_32k_anchor(O):
+    p, st = make_config(O, "cfg3")
+    r = O.compute_lj_cells(p, *st[:3])
+    tu = O.tail_corrections(p)[0]
+    assert r[7] == 864000                       # 54 neighbours/atom on FCC
+    assert abs((r[3] - tu) - (-203671.888067)) < 1e-5
+    assert O.cells_per_edge(p) == 13
+
+
+def test_unwrap_matches_displacement(O):
+    p, st = make_config(O, "cfg1")
+    s = [a.copy() for a in st]
+    ru = [a.copy() for a in s[:3]]
+    O.run_steps(p, 50, s, ru=ru)
+    # unwrapped and wrapped differ by integer multiples of L
+    for w, u in zip(s[:3], ru):
+        k = (u - w) / p.box_length
+        assert np.abs(k - np.round(k)).max() < 1e-9
