@@ -79,7 +79,7 @@ class ClockSampler(threading.Thread):
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
         self.sm_max = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -97,7 +97,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         if self.nv is None:
             return
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
                 r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -109,7 +109,7 @@ class ClockSampler(threading.Thread):
             time.sleep(self.period)
 
     def finish(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
