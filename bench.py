@@ -44,6 +44,7 @@ WORKLOADS = {
     "cfg2": dict(k=10, L=20.0, rc=9.8, dt=1e-4, method="allpairs", T=1.416),
     "cfg3_allpairs": dict(k=20, L=34.19951893353394, rc=2.5, dt=1e-3, method="allpairs", T=1.0),
     "cfg3_cells": dict(k=20, L=34.19951893353394, rc=2.5, dt=1e-3, method="cells", T=1.0),
+    "dense32k": dict(k=20, L=40.0, rc=19.6, dt=1e-4, method="allpairs", T=1.416),  # tuning only
     "cfg4_cells": dict(k=64, L=109.4384605873086, rc=2.5, dt=1e-3, method="cells", T=1.0),
 }
 

@@ -14,7 +14,7 @@ int cells_per_edge_host(const ljmd_params &p)
 
 int cellwork_plan(ljmd_ctx *) { return set_error(LJMD_ERR_UNSUPPORTED, "cell list not built yet"); }
 void cellwork_free(ljmd_ctx *) {}
-int launch_cells_force(ljmd_ctx *) { return set_error(LJMD_ERR_UNSUPPORTED, "cell list not built yet"); }
+int launch_cells_force(ljmd_ctx *, int) { return set_error(LJMD_ERR_UNSUPPORTED, "cell list not built yet"); }
 
 } // namespace ljmd
 

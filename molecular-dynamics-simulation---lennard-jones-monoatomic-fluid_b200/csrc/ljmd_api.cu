@@ -76,7 +76,6 @@ static void refresh_constants(ljmd_ctx *c)
 static void drop_graphs(ljmd_ctx *c)
 {
     if (c->graph_chunk) { cudaGraphExecDestroy(c->graph_chunk); c->graph_chunk = nullptr; }
-    if (c->graph_one) { cudaGraphExecDestroy(c->graph_one); c->graph_one = nullptr; }
 }
 
 struct DeviceGuard {
@@ -91,31 +90,34 @@ struct DeviceGuard {
     ~DeviceGuard() { if (active) cudaSetDevice(prev); }
 };
 
-static int enqueue_force(ljmd_ctx *c)
+static int enqueue_force(ljmd_ctx *c, int buf)
 {
-    if (c->method == LJMD_METHOD_CELLS) return launch_cells_force(c);
-    return launch_pairs(c);
+    if (c->method == LJMD_METHOD_CELLS) return launch_cells_force(c, buf);
+    return launch_pairs(c, buf);
 }
 
-static int kernels_per_step(const ljmd_ctx *c) { return (c->method == LJMD_METHOD_CELLS) ? 6 : 3; }
+static int kernels_per_step(const ljmd_ctx *c) { return (c->method == LJMD_METHOD_CELLS) ? c->cw.kernels_per_force + 1 : 2; }
 
-static int enqueue_step(ljmd_ctx *c)
+// One velocity-Verlet step.  On entry rbuf[prev] holds r(t) and rbuf[1-prev] already holds the
+// drifted + wrapped r(t+dt).  fin_mode 1 leaves r(t+2dt) in rbuf[prev]; fin_mode 2 copies r(t+dt)
+// into rbuf[prev] instead (used for the last step of an odd-length run so that rbuf[0] is current).
+static int enqueue_step(ljmd_ctx *c, int prev, int fin_mode)
 {
-    LJMD_TRY(launch_verlet_pre(c));
-    LJMD_TRY(enqueue_force(c));
-    LJMD_TRY(launch_finalize(c, true));
+    const int now = 1 - prev;
+    LJMD_TRY(enqueue_force(c, now));
+    LJMD_TRY(launch_finalize(c, fin_mode, prev, now, prev));
     return LJMD_OK;
 }
 
 static int capture_graph(ljmd_ctx *c, int nsteps, cudaGraphExec_t *out)
 {
     cudaGraph_t g = nullptr;
-    const int64_t saved = c->launches;
     LJMD_CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    c->capturing = true;
     int rc = LJMD_OK;
-    for (int s = 0; s < nsteps && rc == LJMD_OK; ++s) rc = enqueue_step(c);
+    for (int s = 0; s < nsteps && rc == LJMD_OK; ++s) rc = enqueue_step(c, s & 1, 1);
+    c->capturing = false;
     cudaError_t e = cudaStreamEndCapture(c->stream, &g);
-    c->launches = saved; // captured, not executed
     if (rc != LJMD_OK) { if (g) cudaGraphDestroy(g); return rc; }
     LJMD_CUDA_CHECK(e);
     e = cudaGraphInstantiate(out, g, 0);
@@ -145,15 +147,20 @@ static int set_ctl(ljmd_ctx *c, long long cap, double *series)
     return LJMD_OK;
 }
 
+// nsteps velocity-Verlet steps.  Invariant outside this function: rbuf[0] (the state block's
+// rx..rz) holds the current positions.
 static int run_steps(ljmd_ctx *c, int nsteps)
 {
+    if (nsteps <= 0) return LJMD_OK;
+    LJMD_TRY(launch_drift(c, 0, 1)); // r(t+dt) of the first step
+    int done = 0;
     if (c->timing) {
-        for (int s = 0; s < nsteps; ++s) {
-            LJMD_TRY(launch_verlet_pre(c));
+        for (; done < nsteps; ++done) {
+            const int prev = done & 1, last = (done == nsteps - 1);
             LJMD_CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
-            LJMD_TRY(enqueue_force(c));
+            LJMD_TRY(enqueue_force(c, 1 - prev));
             LJMD_CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
-            LJMD_TRY(launch_finalize(c, true));
+            LJMD_TRY(launch_finalize(c, (last && prev == 0) ? 2 : 1, prev, 1 - prev, prev));
             LJMD_CUDA_CHECK(cudaEventSynchronize(c->ev1));
             float ms = 0.f;
             LJMD_CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
@@ -162,26 +169,20 @@ static int run_steps(ljmd_ctx *c, int nsteps)
         }
         return LJMD_OK;
     }
-    if (nsteps <= 2) {
-        for (int s = 0; s < nsteps; ++s) LJMD_TRY(enqueue_step(c));
-        return LJMD_OK;
+    const int G = 32; // even, so a chunk starts and ends with rbuf[0] = r(t)
+    if (nsteps >= G) {
+        if (!c->graph_chunk) {
+            LJMD_TRY(capture_graph(c, G, &c->graph_chunk));
+            c->graph_chunk_steps = G;
+        }
+        for (; done + G <= nsteps; done += G) {
+            LJMD_CUDA_CHECK(cudaGraphLaunch(c->graph_chunk, c->stream));
+            c->launches += (int64_t)G * kernels_per_step(c);
+        }
     }
-    const int G = 32;
-    if (nsteps >= G && !c->graph_chunk) {
-        LJMD_TRY(capture_graph(c, G, &c->graph_chunk));
-        c->graph_chunk_steps = G;
-    }
-    if (!c->graph_one) LJMD_TRY(capture_graph(c, 1, &c->graph_one));
-    int left = nsteps;
-    while (left >= G) {
-        LJMD_CUDA_CHECK(cudaGraphLaunch(c->graph_chunk, c->stream));
-        c->launches += (int64_t)G * kernels_per_step(c);
-        left -= G;
-    }
-    while (left > 0) {
-        LJMD_CUDA_CHECK(cudaGraphLaunch(c->graph_one, c->stream));
-        c->launches += kernels_per_step(c);
-        left -= 1;
+    for (; done < nsteps; ++done) {
+        const int prev = done & 1, last = (done == nsteps - 1);
+        LJMD_TRY(enqueue_step(c, prev, (last && prev == 0) ? 2 : 1));
     }
     return LJMD_OK;
 }
@@ -267,6 +268,8 @@ extern "C" int ljmd_ctx_destroy(ljmd_ctx *c)
     cudaFree(c->state_block);
     cudaFree(c->pw.fpart);
     cudaFree(c->pw.spart);
+    cudaFree(c->pw.fJ);
+    cudaFree(c->pw.items);
     cudaFree(c->fw.kpart);
     cudaFree(c->fw.counter);
     cudaFree(c->fw.ctl);
@@ -351,9 +354,9 @@ extern "C" int ljmd_ctx_create(const ljmd_params *params, const ljmd_options *op
     CREATE_CHECK(cudaEventCreate(&c->ev_s1));
     refresh_constants(c);
 
-    // state block: 9 arrays | obs[R][4] | (ru: 3 arrays)
+    // state block: 9 arrays | obs[R][4] | alt positions (3 arrays) | (ru: 3 arrays)
     const bool track = (o.flags & LJMD_FLAG_TRACK_UNWRAPPED) != 0;
-    const size_t ndoubles = 9 * c->nR + 4 * (size_t)c->R + (track ? 3 * c->nR : 0);
+    const size_t ndoubles = 12 * c->nR + 4 * (size_t)c->R + (track ? 3 * c->nR : 0);
     CREATE_CHECK(cudaMalloc(&c->state_block, sizeof(double) * ndoubles));
     CREATE_CHECK(cudaMemsetAsync(c->state_block, 0, sizeof(double) * ndoubles, c->stream)); // zero_state, md_types.f90:222-230
     double *b = c->state_block;
@@ -361,13 +364,17 @@ extern "C" int ljmd_ctx_create(const ljmd_params *params, const ljmd_options *op
     c->st.vx = b + 3 * c->nR; c->st.vy = b + 4 * c->nR; c->st.vz = b + 5 * c->nR;
     c->st.ax = b + 6 * c->nR; c->st.ay = b + 7 * c->nR; c->st.az = b + 8 * c->nR;
     c->fw.obs = b + 9 * c->nR;
+    c->rbuf[0] = b;
+    c->rbuf[1] = b + 9 * c->nR + 4 * (size_t)c->R;
     if (track) {
-        double *u = b + 9 * c->nR + 4 * (size_t)c->R;
+        double *u = b + 12 * c->nR + 4 * (size_t)c->R;
         c->st.rux = u; c->st.ruy = u + c->nR; c->st.ruz = u + 2 * c->nR;
     }
 
     c->fw.block = 256;
-    c->fw.nblk = (params->n + c->fw.block - 1) / c->fw.block;
+    // small systems: 8 thread groups share each atom's partial sum (many partials, few atoms)
+    c->fw.groups = (method == LJMD_METHOD_ALLPAIRS && params->n <= 65536) ? 8 : 1;
+    c->fw.nblk = (params->n + (256 / c->fw.groups) - 1) / (256 / c->fw.groups);
     CREATE_CHECK(cudaMalloc(&c->fw.kpart, sizeof(double) * 3 * (size_t)c->fw.nblk * c->R));
     CREATE_CHECK(cudaMalloc(&c->fw.counter, sizeof(unsigned) * (c->R + 1)));
     CREATE_CHECK(cudaMemsetAsync(c->fw.counter, 0, sizeof(unsigned) * (c->R + 1), c->stream));
@@ -463,8 +470,8 @@ extern "C" int ljmd_ctx_compute_forces(ljmd_ctx *c, double *obs3)
     if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_compute_forces(): ctx is NULL.");
     DeviceGuard g;
     LJMD_TRY(g.enter(c->device));
-    LJMD_TRY(enqueue_force(c));
-    LJMD_TRY(launch_finalize(c, false));
+    LJMD_TRY(enqueue_force(c, 0));
+    LJMD_TRY(launch_finalize(c, 0, 0, 0, 0));
     const int idx[3] = {0, 2, 3};
     return fetch_obs(c, obs3, 3, idx);
 }
@@ -559,7 +566,7 @@ extern "C" int ljmd_ctx_pair_counts(ljmd_ctx *c, int64_t *n_candidates, int64_t 
     LJMD_TRY(g.enter(c->device));
     if (!c->fw.pair_counts) LJMD_CUDA_CHECK(cudaMalloc(&c->fw.pair_counts, 2 * sizeof(unsigned long long) * c->R));
     LJMD_CUDA_CHECK(cudaMemsetAsync(c->fw.pair_counts, 0, 2 * sizeof(unsigned long long) * c->R, c->stream));
-    int rc = enqueue_force(c); // positions unchanged: recomputes the same partials, plus counts
+    int rc = enqueue_force(c, 0); // positions unchanged: recomputes the same partials, plus counts
     unsigned long long h[2] = {0, 0};
     if (rc == LJMD_OK) {
         cudaError_t e = cudaMemcpyAsync(h, c->fw.pair_counts, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
@@ -645,8 +652,8 @@ extern "C" int ljmd_compute_lj(const ljmd_params *params, const double *rx, cons
     memcpy(c->h_stage + c->nR, ry, nb);
     memcpy(c->h_stage + 2 * c->nR, rz, nb);
     LJMD_CUDA_CHECK(cudaMemcpyAsync(c->st.rx, c->h_stage, 3 * nb, cudaMemcpyHostToDevice, c->stream));
-    LJMD_TRY(enqueue_force(c));
-    LJMD_TRY(launch_finalize(c, false));
+    LJMD_TRY(enqueue_force(c, 0));
+    LJMD_TRY(launch_finalize(c, 0, 0, 0, 0));
     // accelerations and obs are contiguous: ax ay az | obs
     LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_stage + 6 * c->nR, c->st.ax, 3 * nb + sizeof(double) * 4,
                                     cudaMemcpyDeviceToHost, c->stream));
@@ -680,7 +687,8 @@ extern "C" int ljmd_verlet_step(const ljmd_params *params, double *rx, double *r
     double *arr[9] = {rx, ry, rz, vx, vy, vz, ax, ay, az};
     for (int k = 0; k < 9; ++k) memcpy(c->h_stage + (size_t)k * c->nR, arr[k], nb);
     LJMD_CUDA_CHECK(cudaMemcpyAsync(c->state_block, c->h_stage, 9 * nb, cudaMemcpyHostToDevice, c->stream));
-    LJMD_TRY(enqueue_step(c));
+    LJMD_TRY(launch_drift(c, 0, 1));
+    LJMD_TRY(enqueue_step(c, 0, 2)); // mode 2: the new positions are copied back into rbuf[0]
     LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_stage, c->state_block, 9 * nb + sizeof(double) * 4,
                                     cudaMemcpyDeviceToHost, c->stream));
     LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));

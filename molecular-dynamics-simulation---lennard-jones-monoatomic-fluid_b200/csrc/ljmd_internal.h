@@ -60,18 +60,28 @@ struct StatePtrs {
 
 // Work buffers of the all-pairs path.
 struct PairWork {
-    int block;       // threads per CTA of the pair kernel
+    int variant;     // 0 = full-matrix kernel, 1 = symmetric-tile kernel (default)
+    // ---- variant 0 ----
+    int block;       // threads per CTA
     int ipt;         // i-atoms per thread
     int n_itiles;    // CTAs along i
-    int n_splits;    // CTAs along j (each handles a contiguous j range)
     int split_len;   // atoms per j split
-    double *fpart;   // [R][n_splits][3][n] partial forces (without the factor 24)
-    double *spart;   // [R][n_itiles*n_splits][3] partial (u, du, ddu) over ORDERED pairs
-    int variant;     // 0 = full-matrix kernel, 1 = symmetric-tile kernel
+    // ---- variant 1 ----
+    int ri, warps;        // i-atoms per lane, warps per CTA (row = ri*32*warps atoms)
+    int n_rows;           // rows of i-atoms
+    int chunks_per_item;  // 32-atom j-chunks per work item
+    int4 *items;          // device work-item table
+    double *fJ;           // [R][n_rows][3][n] j-side partial forces
+    // ---- both ----
+    int n_splits;    // variant 0: j splits; variant 1: max splits of any row
+    int n_items;     // CTAs per replica (= scalar partials per replica)
+    double *fpart;   // variant 0: [R][n_splits][3][n]; variant 1: i-side partials, same shape
+    double *spart;   // [R][n_items][3] scalar partials
 };
 
 struct FinalizeWork {
     int block;          // threads per CTA
+    int groups;         // thread groups sharing one atom's partial sum (1 or 8)
     int nblk;           // CTAs per replica
     double *kpart;      // [R][nblk][3] partial sums of vx^2, vy^2, vz^2
     unsigned *counter;  // [R] last-block tickets
@@ -92,10 +102,13 @@ struct CellWork {
     double *sx, *sy, *sz; // [R][n] positions in cell-sorted order
     double *spart;      // [R][nblk_force][3]
     int nblk_force;
+    int kernels_per_force; // launches per force evaluation (binning + sort + force)
     int block;
     void *scan_tmp;     // scratch for the block scan
     unsigned long long *pair_counts; // [R][2]
     double *fsorted;    // [R][3][n] forces in sorted order (without factor 24)
+    int *slot_of_atom;  // [R][n] inverse of `order`
+    double pair_weight; // 0.5 if the force kernel visits ordered pairs, 1.0 if unordered
 };
 
 } // namespace ljmd
@@ -111,7 +124,11 @@ struct ljmd_ctx {
     cudaStream_t stream;
     ljmd::SimConst sc;
     ljmd::StatePtrs st;
-    double *state_block; // one allocation backing st.* (9 or 12 arrays)
+    double *state_block; // one allocation backing st.*: 9 arrays | obs | alt positions | (ru)
+    double *rbuf[2];     // position buffers (x array; y, z follow at +nR, +2nR).  rbuf[0] is the
+                         // state block's rx..rz and always holds the current positions outside
+                         // of ljmd_ctx_step; rbuf[1] is the ping-pong partner.
+    bool capturing;      // stream capture in progress (launch counters are not advanced)
     ljmd::PairWork pw;
     ljmd::FinalizeWork fw;
     ljmd::CellWork cw;
@@ -120,7 +137,6 @@ struct ljmd_ctx {
     // graphs
     cudaGraphExec_t graph_chunk; // G steps
     int graph_chunk_steps;
-    cudaGraphExec_t graph_one;   // 1 step
     // series buffer
     double *d_series;
     long long series_cap;
@@ -137,21 +153,23 @@ struct ljmd_ctx {
 namespace ljmd {
 
 // ---- verlet.cu ---------------------------------------------------------------------------
-// drift + wrap + first half-kick (+ unwrapped update), verlet.f90:58-74
-int launch_verlet_pre(ljmd_ctx *c);
-// a = 24*sum(partials); optional second half-kick + E_kin (verlet.f90:86-95); scalar reduction
-int launch_finalize(ljmd_ctx *c, bool kick);
+// rbuf[to] = wrap(drift(rbuf[from], v, a)), verlet.f90:58-63
+int launch_drift(ljmd_ctx *c, int from, int to);
+// a = 24*sum(partials) (+ both half kicks, E_kin, ru, next positions); scalar reduction.
+// mode 0: forces only; 1: full step, rbuf[out] = positions of the next step; 2: full step,
+// rbuf[out] = copy of rbuf[now].
+int launch_finalize(ljmd_ctx *c, int mode, int prev, int now, int out);
 int launch_ekin_driver(ljmd_ctx *c, double *d_out);
 int measure_fp64_peak(int device, double *tflops);
 
 // ---- lj_allpairs.cu ----------------------------------------------------------------------
 int pairwork_plan(ljmd_ctx *c);
-int launch_pairs(ljmd_ctx *c);
+int launch_pairs(ljmd_ctx *c, int buf); // positions from rbuf[buf]
 
 // ---- lj_cells.cu -------------------------------------------------------------------------
 int cellwork_plan(ljmd_ctx *c);
 void cellwork_free(ljmd_ctx *c);
-int launch_cells_force(ljmd_ctx *c);
+int launch_cells_force(ljmd_ctx *c, int buf);
 int cells_per_edge_host(const ljmd_params &p);
 
 } // namespace ljmd

@@ -1,6 +1,6 @@
-// verlet.cu -- O(N) kernels of the velocity-Verlet step and the deterministic scalar
-// reductions.  Compiled with -fmad=false: every operation below is rounded exactly as the
-// reference's gfortran -O2 build rounds it (no contraction), in the reference's order.
+// verlet.cu -- O(N) kernels of the velocity-Verlet step and the deterministic reductions.
+// Compiled with -fmad=false: every operation below is rounded exactly as the reference's
+// gfortran -O2 build rounds it (no contraction), in the reference's order.
 //
 // Reference (file:line relative to /root/reference/scripts/):
 //   physics/verlet.f90:58-60   drift        r = (r + v*dt) + a*dt_square_half
@@ -10,105 +10,162 @@
 //   physics/verlet.f90:93-95   E_kin        0.5*(sum(vx^2)+sum(vy^2)+sum(vz^2))
 //   physics/lj_potential_energy.f90:188-223 prefactors 4/24 and tail corrections
 //   md_simulation_program.f90:339-353       unwrapped update ru += MIC(r_new - r_old)
+//
+// Step structure on the device ("Verlet fused into the force epilogue"):
+//   the force kernel reads the positions r(t+dt) from buffer NOW; the finalize kernel then, per
+//   atom, sums the force partials -> a(t+dt), applies BOTH half kicks (v_half = v + a_old*dt/2,
+//   v = v_half + a_new*dt/2: the same two roundings as verlet.f90:72-74,86-88), accumulates E_kin,
+//   updates the unwrapped coordinates, and already writes the drifted + wrapped positions of the
+//   NEXT step into the other position buffer (PREV, no longer needed).  Two launches per step.
 #include "ljmd_internal.h"
 #include "reduce.cuh"
 
 namespace ljmd {
 
-// ------------------------------------------------------------------------------------------
-// drift + wrap + first half kick (+ unwrapped-coordinate update).  One thread per atom.
-// HBM traffic per atom: read r,v,a (72 B) + write r,v (48 B) [+ ru read/write 48 B].
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) verlet_pre_kernel(SimConst sc, StatePtrs st, size_t total)
+__device__ __forceinline__ double drift_wrap(double x, double v, double a, const SimConst &sc)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const double L = sc.L;
+    double xn = (x + v * sc.dt) + a * sc.dt_square_half; // verlet.f90:58
     // geometry_pbc.f90:51 recomputes invL = 1/L locally; same value as params%inv_box_length.
-    const double invL = sc.invL;
-    const double x0 = st.rx[i], y0 = st.ry[i], z0 = st.rz[i];
-    const double vx = st.vx[i], vy = st.vy[i], vz = st.vz[i];
-    const double ax = st.ax[i], ay = st.ay[i], az = st.az[i];
-    double x = (x0 + vx * sc.dt) + ax * sc.dt_square_half; // verlet.f90:58
-    double y = (y0 + vy * sc.dt) + ay * sc.dt_square_half;
-    double z = (z0 + vz * sc.dt) + az * sc.dt_square_half;
-    x = x - L * floor(x * invL); // geometry_pbc.f90:54-56
-    y = y - L * floor(y * invL);
-    z = z - L * floor(z * invL);
-    st.rx[i] = x; st.ry[i] = y; st.rz[i] = z;
-    st.vx[i] = vx + ax * sc.dt_half; // verlet.f90:72-74
-    st.vy[i] = vy + ay * sc.dt_half;
-    st.vz[i] = vz + az * sc.dt_half;
-    if (st.rux) { // md_simulation_program.f90:341-351 (dnint = round half away from zero)
-        double dx = x - x0, dy = y - y0, dz = z - z0;
-        dx = dx - L * round(dx * invL);
-        dy = dy - L * round(dy * invL);
-        dz = dz - L * round(dz * invL);
-        st.rux[i] = st.rux[i] + dx;
-        st.ruy[i] = st.ruy[i] + dy;
-        st.ruz[i] = st.ruz[i] + dz;
-    }
+    return xn - sc.L * floor(xn * sc.invL);              // geometry_pbc.f90:54-56
 }
 
-int launch_verlet_pre(ljmd_ctx *c)
+// ------------------------------------------------------------------------------------------
+// Stand-alone drift + wrap (first step of a ljmd_ctx_step call): dst = wrap(drift(src, v, a)).
+// Velocities are NOT touched here; both half kicks happen in the finalize kernel.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) drift_kernel(SimConst sc, const double *src, double *dst,
+                                                    const double *v, const double *a, size_t total3)
 {
-    const size_t total = c->nR;
-    const int block = 256;
-    const unsigned grid = (unsigned)((total + block - 1) / block);
-    verlet_pre_kernel<<<grid, block, 0, c->stream>>>(c->sc, c->st, total);
-    c->launches++;
+    // src/dst/v/a are the x arrays; y and z follow at stride nR => treat as one array of 3*nR
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total3) return;
+    dst[i] = drift_wrap(src[i], v[i], a[i], sc);
+}
+
+int launch_drift(ljmd_ctx *c, int from, int to)
+{
+    const size_t total3 = 3 * c->nR;
+    const unsigned grid = (unsigned)((total3 + 255) / 256);
+    drift_kernel<<<grid, 256, 0, c->stream>>>(c->sc, c->rbuf[from], c->rbuf[to], c->st.vx, c->st.ax, total3);
+    if (!c->capturing) c->launches++;
     LJMD_CUDA_CHECK(cudaGetLastError());
     return LJMD_OK;
 }
 
 // ------------------------------------------------------------------------------------------
-// Finalize: a_i = 24 * (sum of the force partials of atom i, fixed order), optional second
-// half kick and E_kin partials, then the LAST CTA of each replica reduces every scalar partial
-// in a fixed order and writes {epot, ekin, d_epot, dd_epot}.
-// Which CTA is last varies run to run, but what it computes does not.
+// Finalize.  G thread groups share the partial sums of each atom: group g adds partials
+// g, g+G, g+2G, ... in increasing order, the groups are combined in group order -> fixed order.
+// The LAST CTA of each replica reduces all scalar partials in a fixed order and writes
+// {epot, ekin, d_epot, dd_epot}.  Which CTA is last varies run to run; what it computes does not.
 // ------------------------------------------------------------------------------------------
 struct FinArgs {
     SimConst sc;
-    StatePtrs st;
-    const double *fpart; // [R][n_splits][3][n]
+    size_t nR;
+    // state
+    double *vx, *ax;           // x arrays; y, z at +nR, +2nR
+    double *rux;               // unwrapped x array or nullptr
+    const double *r_prev;      // positions at t       (x array; y,z at +nR,+2nR)
+    const double *r_now;       // positions at t+dt, the ones the force kernel just used
+    double *r_out;             // where r(t+2dt) (or a copy of r_now) is written; may be nullptr
+    int mode;                  // 0: forces only (t=0 call); 1: full step, r_out = next positions;
+                               // 2: full step, r_out = copy of r_now
+    // force partials
+    const double *fpart;       // [R][n_splits][3][n]
     int n_splits;
-    const double *spart; // [R][n_spart][3]
+    int sym;                   // symmetric all-pairs kernel: also sum the j-side partials
+    const double *fJ;          // [R][n_rows][3][n]
+    int n_rows, tcta, chunks_per_item, nchunks;
+    const int *perm;           // cells: fpart is in cell-sorted order; perm[i] = sorted slot of atom i
+    // scalar partials
+    const double *spart;       // [R][n_spart][3]
     int n_spart;
-    double pair_weight;  // 0.5 when spart sums ORDERED pairs, 1.0 for unordered
-    double *kpart;       // [R][gridDim.x][3]
-    unsigned *counter;   // [R]
-    double *obs;         // [R][4]
+    double pair_weight;        // 0.5 when spart sums ORDERED pairs, 1.0 for unordered
+    double *kpart;             // [R][gridDim.x][3]
+    unsigned *counter;         // [R+1]
+    double *obs;               // [R][4]
     StepCtl *ctl;
-    int kick;
 };
 
+template <int G>
 __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
 {
+    constexpr int APB = 256 / G; // atoms per CTA
+    __shared__ double part[G > 1 ? G : 1][3][APB];
     __shared__ double scratch[3 * 8];
     __shared__ bool is_last;
     const int n = a.sc.n;
     const int rep = blockIdx.y;
     const size_t off = (size_t)rep * n;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int la = threadIdx.x % APB, g = threadIdx.x / APB;
+    const int i = blockIdx.x * APB + la;
+
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    if (i < n) {
+        if (a.perm) {
+            const int k = a.perm[off + i];
+            const double *fp = a.fpart + (size_t)rep * 3 * n;
+            if (g == 0) { fx = fp[k]; fy = fp[(size_t)n + k]; fz = fp[2 * (size_t)n + k]; }
+        } else {
+            // partial list of this atom: [j-side rows 0..row] then [i-side splits 0..nsp-1]
+            int nj = 0, nsp = a.n_splits;
+            if (a.sym) {
+                const int row = i / a.tcta;
+                nj = row + 1;
+                const int first = row * a.tcta / 32;
+                nsp = (a.nchunks - first + a.chunks_per_item - 1) / a.chunks_per_item;
+            }
+            const double *fj = a.sym ? a.fJ + (size_t)rep * a.n_rows * 3 * n : nullptr;
+            const double *fp = a.fpart + (size_t)rep * a.n_splits * 3 * n;
+            const int P = nj + nsp;
+#pragma unroll 4
+            for (int p = g; p < P; p += G) {
+                const double *src = (p < nj) ? fj + (size_t)p * 3 * n : fp + (size_t)(p - nj) * 3 * n;
+                fx += src[i];
+                fy += src[(size_t)n + i];
+                fz += src[2 * (size_t)n + i];
+            }
+        }
+    }
+    if (G > 1) {
+        part[g][0][la] = fx; part[g][1][la] = fy; part[g][2][la] = fz;
+        __syncthreads();
+        if (g == 0) {
+            fx = part[0][0][la]; fy = part[0][1][la]; fz = part[0][2][la];
+#pragma unroll
+            for (int q = 1; q < G; ++q) { fx += part[q][0][la]; fy += part[q][1][la]; fz += part[q][2][la]; }
+        }
+    }
 
     double k[3] = {0.0, 0.0, 0.0};
-    if (i < n) {
-        const double *fp = a.fpart + (size_t)rep * a.n_splits * 3 * n;
-        double fx = 0.0, fy = 0.0, fz = 0.0;
-        for (int s = 0; s < a.n_splits; ++s) { // fixed order
-            fx += fp[((size_t)s * 3 + 0) * n + i];
-            fy += fp[((size_t)s * 3 + 1) * n + i];
-            fz += fp[((size_t)s * 3 + 2) * n + i];
+    if (i < n && g == 0) {
+        const size_t ix = off + i, iy = ix + a.nR, iz = iy + a.nR;
+        const double axn = 24.0 * fx, ayn = 24.0 * fy, azn = 24.0 * fz; // lj_potential_energy.f90:189-191
+        double vx = a.vx[ix], vy = a.vx[iy], vz = a.vx[iz];
+        if (a.mode != 0) {
+            const double axo = a.ax[ix], ayo = a.ax[iy], azo = a.ax[iz];
+            vx = vx + axo * a.sc.dt_half; vy = vy + ayo * a.sc.dt_half; vz = vz + azo * a.sc.dt_half; // verlet.f90:72-74
+            vx = vx + axn * a.sc.dt_half; vy = vy + ayn * a.sc.dt_half; vz = vz + azn * a.sc.dt_half; // verlet.f90:86-88
+            a.vx[ix] = vx; a.vx[iy] = vy; a.vx[iz] = vz;
+            const double x = a.r_now[ix], y = a.r_now[iy], z = a.r_now[iz];
+            if (a.rux) { // md_simulation_program.f90:341-351 (dnint = round half away from zero)
+                const double L = a.sc.L, invL = a.sc.invL;
+                double dx = x - a.r_prev[ix], dy = y - a.r_prev[iy], dz = z - a.r_prev[iz];
+                dx = dx - L * round(dx * invL);
+                dy = dy - L * round(dy * invL);
+                dz = dz - L * round(dz * invL);
+                a.rux[ix] = a.rux[ix] + dx; a.rux[iy] = a.rux[iy] + dy; a.rux[iz] = a.rux[iz] + dz;
+            }
+            if (a.r_out) {
+                if (a.mode == 1) { // positions of the next step, verlet.f90:58-63
+                    a.r_out[ix] = drift_wrap(x, vx, axn, a.sc);
+                    a.r_out[iy] = drift_wrap(y, vy, ayn, a.sc);
+                    a.r_out[iz] = drift_wrap(z, vz, azn, a.sc);
+                } else {
+                    a.r_out[ix] = x; a.r_out[iy] = y; a.r_out[iz] = z;
+                }
+            }
         }
-        const double ax = 24.0 * fx, ay = 24.0 * fy, az = 24.0 * fz; // lj_potential_energy.f90:189-191
-        a.st.ax[off + i] = ax; a.st.ay[off + i] = ay; a.st.az[off + i] = az;
-        double vx = a.st.vx[off + i], vy = a.st.vy[off + i], vz = a.st.vz[off + i];
-        if (a.kick) { // verlet.f90:86-88
-            vx = vx + ax * a.sc.dt_half;
-            vy = vy + ay * a.sc.dt_half;
-            vz = vz + az * a.sc.dt_half;
-            a.st.vx[off + i] = vx; a.st.vy[off + i] = vy; a.st.vz[off + i] = vz;
-        }
+        a.ax[ix] = axn; a.ax[iy] = ayn; a.ax[iz] = azn;
         k[0] = vx * vx; k[1] = vy * vy; k[2] = vz * vz; // verlet.f90:93-95
     }
     block_sum<3>(k, scratch);
@@ -123,7 +180,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
     if (!is_last) return;
     __threadfence();
 
-    // Fixed-order reduction of all partials of this replica.
+    // Fixed-order reduction of all scalar partials of this replica.
     double s[3] = {0.0, 0.0, 0.0};
     const double *sp = a.spart + (size_t)rep * a.n_spart * 3;
     for (int b = threadIdx.x; b < a.n_spart; b += blockDim.x) {
@@ -143,6 +200,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
     if (threadIdx.x == 0) {
         const double w = a.pair_weight;
         double o[4];
+        if (a.sym) {
+            // s[0] = sum r^-12, s[1] = sum r^-6 over the in-cutoff unordered pairs:
+            // U/4 = S12 - S6 (:140), dU_r = -2 S12 + S6 (:143), ddU = 26 S12 - 7 S6 (:178)
+            const double S12 = s[0], S6 = s[1];
+            s[0] = S12 - S6;
+            s[1] = fma(-2.0, S12, S6);
+            s[2] = fma(26.0, S12, -7.0 * S6);
+        }
         o[0] = 4.0 * (w * s[0]) + a.sc.tail_u;    // lj_potential_energy.f90:188,221
         o[1] = 0.5 * (kk[0] + kk[1] + kk[2]);     // verlet.f90:93-95
         o[2] = 24.0 * (w * s[1]) + a.sc.tail_du;  // :192,222
@@ -150,14 +215,13 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
         double *ob = a.obs + 4 * (size_t)rep;
         ob[0] = o[0]; ob[1] = o[1]; ob[2] = o[2]; ob[3] = o[3];
         StepCtl *ctl = a.ctl;
-        if (a.kick) {
-            const long long step = ctl->step;
+        if (a.mode != 0) {
+            const long long step = *((volatile long long *)&ctl->step);
             if (ctl->series && step < ctl->series_cap) {
                 double *sr = ctl->series + ((size_t)step * gridDim.y + rep) * 4;
                 sr[0] = o[0]; sr[1] = o[1]; sr[2] = o[2]; sr[3] = o[3];
             }
-            // the replica with the highest index that finishes bumps the step: use a ticket
-            // so that exactly one CTA per step does it after all replicas wrote their row.
+            // the last replica to get here bumps the step counter (every replica has read it)
             __threadfence();
             const unsigned t2 = atomicAdd(&a.counter[gridDim.y], 1u);
             if (t2 == gridDim.y - 1) {
@@ -169,24 +233,51 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
     }
 }
 
-int launch_finalize(ljmd_ctx *c, bool kick)
+// mode 0: forces only; mode 1: step, write next positions into rbuf[out]; mode 2: step, copy
+// rbuf[now] into rbuf[out].
+int launch_finalize(ljmd_ctx *c, int mode, int prev, int now, int out)
 {
     FinArgs a;
     a.sc = c->sc;
-    a.st = c->st;
-    a.fpart = c->pw.fpart;
-    a.n_splits = c->pw.n_splits;
-    a.spart = c->pw.spart;
-    a.n_spart = c->pw.n_itiles * c->pw.n_splits;
-    a.pair_weight = (c->pw.variant == 0) ? 0.5 : 1.0;
+    a.nR = c->nR;
+    a.vx = c->st.vx;
+    a.ax = c->st.ax;
+    a.rux = c->st.rux;
+    a.r_prev = c->rbuf[prev];
+    a.r_now = c->rbuf[now];
+    a.r_out = (mode == 0) ? nullptr : c->rbuf[out];
+    a.mode = mode;
+    a.perm = nullptr;
+    if (c->method == LJMD_METHOD_CELLS) {
+        a.fpart = c->cw.fsorted;
+        a.n_splits = 1;
+        a.sym = 0;
+        a.perm = c->cw.slot_of_atom;
+        a.spart = c->cw.spart;
+        a.n_spart = c->cw.nblk_force;
+        a.pair_weight = c->cw.pair_weight;
+        a.fJ = nullptr; a.n_rows = 0; a.tcta = 1; a.chunks_per_item = 1; a.nchunks = 0;
+    } else {
+        a.fpart = c->pw.fpart;
+        a.n_splits = c->pw.n_splits;
+        a.sym = (c->pw.variant == 1) ? 1 : 0;
+        a.fJ = c->pw.fJ;
+        a.n_rows = c->pw.n_rows;
+        a.tcta = c->pw.ri * 32 * c->pw.warps;
+        a.chunks_per_item = c->pw.chunks_per_item;
+        a.nchunks = (c->sc.n + 31) / 32;
+        a.spart = c->pw.spart;
+        a.n_spart = c->pw.n_items;
+        a.pair_weight = (c->pw.variant == 0) ? 0.5 : 1.0;
+    }
     a.kpart = c->fw.kpart;
     a.counter = c->fw.counter;
     a.obs = c->fw.obs;
     a.ctl = c->fw.ctl;
-    a.kick = kick ? 1 : 0;
     dim3 grid(c->fw.nblk, c->R);
-    finalize_kernel<<<grid, c->fw.block, 0, c->stream>>>(a);
-    c->launches++;
+    if (c->fw.groups == 8) finalize_kernel<8><<<grid, 256, 0, c->stream>>>(a);
+    else finalize_kernel<1><<<grid, 256, 0, c->stream>>>(a);
+    if (!c->capturing) c->launches++;
     LJMD_CUDA_CHECK(cudaGetLastError());
     return LJMD_OK;
 }
