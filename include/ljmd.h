@@ -180,6 +180,12 @@ int ljmd_ctx_download_cells(ljmd_ctx *ctx, int32_t *cell_of_atom, int32_t *cell_
 /* Unordered candidate pairs distance-tested / in-cutoff pairs of the last force evaluation. */
 int ljmd_ctx_pair_counts(ljmd_ctx *ctx, int64_t *n_candidates, int64_t *n_in_cutoff);
 
+/* Self-benchmark of the symmetric all-pairs inner routine: cycles per (32 x 32*ri)-pair tile
+ * divided by 32, for ri i-atoms per lane and rj rotation offsets per step, seen by one warp when
+ * warps_per_cta warps share each SM.  Tuning aid (tools/chunk_cycles.py). */
+int ljmd_bench_chunk_cycles(int32_t ri, int32_t rj, int32_t dense, int32_t warps_per_cta,
+                            double *cycles_per_step);
+
 /* Measured FP64 FMA throughput of the device the context lives on (register-resident DFMA
  * chains), in TFLOP/s; the roofline denominator for the all-pairs kernel. */
 int ljmd_measure_fp64_peak(int32_t device, double *tflops);

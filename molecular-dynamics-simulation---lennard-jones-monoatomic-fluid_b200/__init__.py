@@ -84,7 +84,7 @@ ABI_SYMBOLS = [
     "ljmd_ctx_compute_forces", "ljmd_ctx_step", "ljmd_ctx_step_series",
     "ljmd_ctx_kinetic_energy", "ljmd_ctx_method", "ljmd_ctx_cells_per_edge",
     "ljmd_ctx_launch_count", "ljmd_ctx_last_step_ms", "ljmd_ctx_force_timing", "ljmd_ctx_download_cells",
-    "ljmd_ctx_pair_counts", "ljmd_measure_fp64_peak",
+    "ljmd_ctx_pair_counts", "ljmd_measure_fp64_peak", "ljmd_bench_chunk_cycles",
 ]
 
 
@@ -194,6 +194,12 @@ def verlet_step(params: SimParams, state: SimState):
 
 def compat_release() -> None:
     _chk(load_library().ljmd_compat_release())
+
+
+def bench_chunk_cycles(ri: int, rj: int, dense: bool, warps_per_cta: int) -> float:
+    c = C.c_double()
+    _chk(load_library().ljmd_bench_chunk_cycles(ri, rj, 1 if dense else 0, warps_per_cta, C.byref(c)))
+    return c.value
 
 
 def measure_fp64_peak(device: int = -1) -> float:

@@ -126,6 +126,7 @@ struct SymArgs {
     double *spart;              // [R][n_items][3]        (S12, S6, unused)
     int max_splits, n_rows;
     unsigned long long *pair_counts; // optional [2]
+    long long *dbg;                  // optional per-warp {start, end, smid, items} (tuning)
 };
 
 // 1/x to <= 1 ulp: MUFU.RCP64H seed (relative error < 2^-20) and one cubic (Halley) step,
@@ -139,60 +140,96 @@ __device__ __forceinline__ double fast_rcp(double x)
     return fma(y0, t, y0);
 }
 
-// One 32-atom j-chunk against the RI*32 i-atoms of a warp: 32 rotation steps.
-// The distance stage of the RI pairs of a step is computed first (RI independent dependency
-// chains), then one branch-free interaction body handles all of them: a pair outside the cutoff
-// contributes exact zeros (its 1/r^2 is replaced by 0), so no per-pair branch serialises the
-// chains.  The body is skipped only when no pair of the step is inside the cutoff.
-template <int RI, bool DIAG, bool COUNT>
+// One 32-atom j-chunk against the RI*32 i-atoms of a warp.
+//
+// Rotation with RJ offsets per step: at step s (s = 0 .. 32/RJ - 1) lane l meets the RJ j-atoms
+// (l + s + q*32/RJ) & 31, q = 0..RJ-1, so every step carries RI*RJ independent pair evaluations
+// (the instruction-level parallelism a single warp needs: measured 252 / 355 / 490 cycles per
+// step for 1 / 2 / 4 pairs, tools/chunk_cycles.py) and a chunk needs only 32/RJ serial steps.
+// Each offset q has its own j-side accumulator set that rotates one lane per step (SHFL); at
+// the end the RJ copies of every j-atom's force are gathered in the fixed order q = 0..RJ-1.
+//
+// The interaction body is branch-free: a pair outside the cutoff contributes exact zeros (its
+// 1/r^2 is replaced by 0), so no per-pair branch serialises the dependency chains.  Unless
+// DENSE, the body is skipped when no pair of the step is inside the cutoff.
+template <int RI, int RJ, bool DIAG, bool DENSE, bool COUNT>
 __device__ __forceinline__ void sym_chunk(const double (*sjb)[32], const double (&xi)[RI], const double (&yi)[RI],
                                           const double (&zi)[RI], double (&fxi)[RI], double (&fyi)[RI],
-                                          double (&fzi)[RI], double &fjx, double &fjy, double &fjz, double &s12,
-                                          double &s6, unsigned &ncut, double L, double invL, double rc2, int lane,
-                                          int iw0, int j0, int n)
+                                          double (&fzi)[RI], double &fjx_out, double &fjy_out, double &fjz_out,
+                                          double &s12, double &s6, unsigned &ncut, double L, double invL, double rc2,
+                                          int lane, int iw0, int j0, int n)
 {
+    constexpr int NS = 32 / RJ;
+    double fjx[RJ], fjy[RJ], fjz[RJ];
+#pragma unroll
+    for (int q = 0; q < RJ; ++q) { fjx[q] = 0.0; fjy[q] = 0.0; fjz[q] = 0.0; }
 #pragma unroll 2
-    for (int s = 0; s < 32; ++s) {
-        const int jj = (lane + s) & 31;
-        const double xj = sjb[0][jj], yj = sjb[1][jj], zj = sjb[2][jj];
-        double dx[RI], dy[RI], dz[RI], r2[RI];
-        bool in[RI];
+    for (int s = 0; s < NS; ++s) {
+        double dx[RJ][RI], dy[RJ][RI], dz[RJ][RI], r2[RJ][RI];
+        bool in[RJ][RI];
         bool any = false;
 #pragma unroll
-        for (int r = 0; r < RI; ++r) {
-            dx[r] = mic(xi[r] - xj, L, invL); // lj_potential_energy.f90:119-126
-            dy[r] = mic(yi[r] - yj, L, invL);
-            dz[r] = mic(zi[r] - zj, L, invL);
-            r2[r] = dist2(dx[r], dy[r], dz[r]); // :129, reference operation order
-            in[r] = r2[r] < rc2;                // :132
-            if (DIAG) {
-                const int ig = iw0 + r * 32 + lane, jg = j0 + jj;
-                in[r] = in[r] && (jg > ig) && (jg < n);
-            }
-            any = any || in[r];
-        }
-        if (any) {
+        for (int q = 0; q < RJ; ++q) {
+            const int jj = (lane + s + q * NS) & 31;
+            const double xj = sjb[0][jj], yj = sjb[1][jj], zj = sjb[2][jj];
 #pragma unroll
             for (int r = 0; r < RI; ++r) {
-                double ir2 = fast_rcp(in[r] ? r2[r] : 1.0);
-                ir2 = in[r] ? ir2 : 0.0;
-                const double ir6 = __dmul_rn(__dmul_rn(ir2, ir2), ir2);
-                const double ir12 = __dmul_rn(ir6, ir6);
-                s12 = __dadd_rn(s12, ir12);
-                s6 = __dadd_rn(s6, ir6);
-                const double g = __dmul_rn(fma(2.0, ir12, -ir6), ir2); // -dU_r / r^2  (:143,148)
-                fxi[r] = fma(g, dx[r], fxi[r]); fyi[r] = fma(g, dy[r], fyi[r]); fzi[r] = fma(g, dz[r], fzi[r]);
-                fjx = fma(-g, dx[r], fjx); fjy = fma(-g, dy[r], fjy); fjz = fma(-g, dz[r], fjz);
-                if (COUNT) ncut += in[r] ? 1u : 0u;
+                dx[q][r] = mic(xi[r] - xj, L, invL); // lj_potential_energy.f90:119-126
+                dy[q][r] = mic(yi[r] - yj, L, invL);
+                dz[q][r] = mic(zi[r] - zj, L, invL);
+                r2[q][r] = dist2(dx[q][r], dy[q][r], dz[q][r]); // :129, reference operation order
+                in[q][r] = r2[q][r] < rc2;                      // :132
+                if (DIAG) {
+                    const int ig = iw0 + r * 32 + lane, jg = j0 + jj;
+                    in[q][r] = in[q][r] && (jg > ig) && (jg < n);
+                }
+                any = any || in[q][r];
             }
         }
-        fjx = __shfl_sync(0xffffffffu, fjx, (lane + 1) & 31);
-        fjy = __shfl_sync(0xffffffffu, fjy, (lane + 1) & 31);
-        fjz = __shfl_sync(0xffffffffu, fjz, (lane + 1) & 31);
+        if (DENSE || any) {
+#pragma unroll
+            for (int q = 0; q < RJ; ++q) {
+#pragma unroll
+                for (int r = 0; r < RI; ++r) {
+                    // r2 = 0 can only occur on the diagonal (self pair); elsewhere r2 >= rc2 > 0
+                    // is finite, its reciprocal is finite and is discarded by the select below.
+                    double ir2 = fast_rcp((DIAG && !in[q][r]) ? 1.0 : r2[q][r]);
+                    ir2 = in[q][r] ? ir2 : 0.0;
+                    const double ir6 = __dmul_rn(__dmul_rn(ir2, ir2), ir2);
+                    const double ir12 = __dmul_rn(ir6, ir6);
+                    s12 = __dadd_rn(s12, ir12);
+                    s6 = __dadd_rn(s6, ir6);
+                    const double g = __dmul_rn(fma(2.0, ir12, -ir6), ir2); // -dU_r / r^2  (:143,148)
+                    fxi[r] = fma(g, dx[q][r], fxi[r]); fyi[r] = fma(g, dy[q][r], fyi[r]); fzi[r] = fma(g, dz[q][r], fzi[r]);
+                    fjx[q] = fma(-g, dx[q][r], fjx[q]); fjy[q] = fma(-g, dy[q][r], fjy[q]); fjz[q] = fma(-g, dz[q][r], fjz[q]);
+                    if (COUNT) ncut += in[q][r] ? 1u : 0u;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < RJ; ++q) {
+            fjx[q] = __shfl_sync(0xffffffffu, fjx[q], (lane + 1) & 31);
+            fjy[q] = __shfl_sync(0xffffffffu, fjy[q], (lane + 1) & 31);
+            fjz[q] = __shfl_sync(0xffffffffu, fjz[q], (lane + 1) & 31);
+        }
+    }
+    // copy q of j-atom m now sits in lane (m - (q+1)*NS) & 31; gather in the order q = 0..RJ-1
+    if (RJ == 1) {
+        fjx_out = fjx[0]; fjy_out = fjy[0]; fjz_out = fjz[0];
+    } else {
+        double tx = 0.0, ty = 0.0, tz = 0.0;
+#pragma unroll
+        for (int q = 0; q < RJ; ++q) {
+            const int src = (lane - (q + 1) * NS) & 31;
+            tx += __shfl_sync(0xffffffffu, fjx[q], src);
+            ty += __shfl_sync(0xffffffffu, fjy[q], src);
+            tz += __shfl_sync(0xffffffffu, fjz[q], src);
+        }
+        fjx_out = tx; fjy_out = ty; fjz_out = tz;
     }
 }
 
-template <int RI, int W, bool COUNT>
+template <int RI, int RJ, int W, bool DENSE, bool COUNT>
 __global__ void __launch_bounds__(W * 32) lj_pairs_sym_kernel(SymArgs a)
 {
     constexpr int TI = RI * 32; // i-atoms per warp
@@ -260,10 +297,10 @@ __global__ void __launch_bounds__(W * 32) lj_pairs_sym_kernel(SymArgs a)
         const bool all = (j0 >= iw0 + TI) && (j0 + 32 <= n);
         if (!none) {
             if (all)
-                sym_chunk<RI, false, COUNT>(sj[buf], xi, yi, zi, fxi, fyi, fzi, fjx, fjy, fjz, s12, s6, ncut,
+                sym_chunk<RI, RJ, false, DENSE, COUNT>(sj[buf], xi, yi, zi, fxi, fyi, fzi, fjx, fjy, fjz, s12, s6, ncut,
                                             L, invL, rc2, lane, iw0, j0, n);
             else
-                sym_chunk<RI, true, COUNT>(sj[buf], xi, yi, zi, fxi, fyi, fzi, fjx, fjy, fjz, s12, s6, ncut,
+                sym_chunk<RI, RJ, true, DENSE, COUNT>(sj[buf], xi, yi, zi, fxi, fyi, fzi, fjx, fjy, fjz, s12, s6, ncut,
                                            L, invL, rc2, lane, iw0, j0, n);
         }
         // after 32 rotations lane l again holds the accumulator of j-atom j0 + l
@@ -312,21 +349,199 @@ __global__ void __launch_bounds__(W * 32) lj_pairs_sym_kernel(SymArgs a)
 }
 
 // ------------------------------------------------------------------------------------------
+// "Independent warps" flavour of the symmetric kernel (rows of RI*32 atoms, W = 1 geometry):
+// a CTA is just NW warps that never synchronise with each other.  Warp g of the launch takes the
+// work items g, g + (number of warps), ... ; consecutive items go to different SMs.  Each warp
+// stages its j-chunks in a private shared-memory slot (__syncwarp only) and writes the j-side
+// partial of a chunk straight from registers.  Few fat CTAs instead of thousands of one-warp
+// CTAs: no CTA-launch ramp, no barrier stalls.  Outputs are indexed by work item, so the result
+// does not depend on which warp ran an item.
+// ------------------------------------------------------------------------------------------
+template <int RI, int RJ, bool DENSE, bool COUNT>
+__global__ void __launch_bounds__(512) lj_pairs_symw_kernel(SymArgs a, int n_items)
+{
+    constexpr int TI = RI * 32;
+    constexpr int MAXW = 16; // warps per CTA is a launch parameter (<= 16: 128 registers/thread)
+    __shared__ double sj[MAXW][2][3][32];
+    __shared__ double scratch[3 * MAXW];
+    const int NW = blockDim.x >> 5;
+
+    const int n = a.sc.n;
+    const int rep = blockIdx.y;
+    const double *rx = a.rx + (size_t)rep * n, *ry = a.ry + (size_t)rep * n,
+                 *rz = a.rz + (size_t)rep * n;
+    const double L = a.sc.L, invL = a.sc.invL, rc2 = a.sc.rc2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double (*sjw)[3][32] = sj[warp];
+
+    double s12 = 0.0, s6 = 0.0;
+    unsigned ncut = 0;
+    const int nwarps_total = gridDim.x * NW;
+    long long t_start = 0;
+    int n_done = 0, n_diag = 0;
+    if (a.dbg) t_start = clock64();
+    for (int it = warp * gridDim.x + blockIdx.x; it < n_items; it += nwarps_total) {
+        ++n_done;
+        const int4 item = a.items[it];
+        const int row = item.x, chunk0 = item.y, nchunks = item.z, split = item.w;
+        const int iw0 = row * TI;
+        double xi[RI], yi[RI], zi[RI], fxi[RI], fyi[RI], fzi[RI];
+#pragma unroll
+        for (int r = 0; r < RI; ++r) {
+            const int ig = iw0 + r * 32 + lane;
+            const bool v = ig < n;
+            xi[r] = v ? rx[ig] : 0.0; yi[r] = v ? ry[ig] : 0.0; zi[r] = v ? rz[ig] : 0.0;
+            fxi[r] = 0.0; fyi[r] = 0.0; fzi[r] = 0.0;
+        }
+        {
+            const int jg = chunk0 * 32 + lane;
+            const bool v = jg < n;
+            __syncwarp();
+            sjw[0][0][lane] = v ? rx[jg] : 0.0;
+            sjw[0][1][lane] = v ? ry[jg] : 0.0;
+            sjw[0][2][lane] = v ? rz[jg] : 0.0;
+            __syncwarp();
+        }
+        for (int k = 0; k < nchunks; ++k) {
+            const int buf = k & 1;
+            const int j0 = (chunk0 + k) * 32;
+            double px = 0.0, py = 0.0, pz = 0.0; // next chunk, in flight during the compute
+            if (k + 1 < nchunks) {
+                const int jg = j0 + 32 + lane;
+                if (jg < n) { px = rx[jg]; py = ry[jg]; pz = rz[jg]; }
+            }
+            double fjx = 0.0, fjy = 0.0, fjz = 0.0;
+            const bool all = (j0 >= iw0 + TI) && (j0 + 32 <= n);
+            if (!all) n_diag++;
+            if (all)
+                sym_chunk<RI, RJ, false, DENSE, COUNT>(sjw[buf], xi, yi, zi, fxi, fyi, fzi, fjx, fjy, fjz, s12, s6,
+                                                   ncut, L, invL, rc2, lane, iw0, j0, n);
+            else
+                sym_chunk<RI, RJ, true, DENSE, COUNT>(sjw[buf], xi, yi, zi, fxi, fyi, fzi, fjx, fjy, fjz, s12, s6,
+                                                  ncut, L, invL, rc2, lane, iw0, j0, n);
+            // lane l holds the j-side force of atom j0 + l again
+            const int jg = j0 + lane;
+            if (jg < n) {
+                double *fj = a.fJ + ((size_t)rep * a.n_rows + row) * 3 * n;
+                fj[jg] = fjx; fj[(size_t)n + jg] = fjy; fj[2 * (size_t)n + jg] = fjz;
+            }
+            if (k + 1 < nchunks) {
+                sjw[buf ^ 1][0][lane] = px; sjw[buf ^ 1][1][lane] = py; sjw[buf ^ 1][2][lane] = pz;
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int r = 0; r < RI; ++r) {
+            const int ig = iw0 + r * 32 + lane;
+            if (ig < n) {
+                double *fp = a.fI + ((size_t)rep * a.max_splits + split) * 3 * n;
+                fp[ig] = fxi[r]; fp[(size_t)n + ig] = fyi[r]; fp[2 * (size_t)n + ig] = fzi[r];
+            }
+        }
+    }
+    if (a.dbg && lane == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        long long *d = a.dbg + 4 * ((size_t)blockIdx.x * NW + warp);
+        d[0] = t_start; d[1] = clock64(); d[2] = smid; d[3] = n_done + 256 * n_diag;
+    }
+    double s[3] = {s12, s6, 0.0};
+    block_sum<3>(s, scratch);
+    if (threadIdx.x == 0) {
+        double *sp = a.spart + ((size_t)rep * gridDim.x + blockIdx.x) * 3;
+        sp[0] = s[0]; sp[1] = s[1]; sp[2] = 0.0;
+    }
+    if (COUNT) {
+        const unsigned c = __reduce_add_sync(0xffffffffu, ncut);
+        if (lane == 0 && a.pair_counts) atomicAdd(&a.pair_counts[1], (unsigned long long)c);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Self-benchmark of the inner routine: `nw` warps per CTA, one CTA per SM, each warp runs
+// `reps` chunks (32 rotation steps each) on synthetic in-cutoff data; reports the cycles per
+// rotation step seen by warp 0 of CTA 0 (clock64).  Used to size RI / warps per SM.
+// ------------------------------------------------------------------------------------------
+template <int RI, int RJ, bool DENSE>
+__global__ void sym_chunk_bench_kernel(double *out, long long *cycles, int reps, double L, double rc2)
+{
+    __shared__ double sj[32][3][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double xi[RI], yi[RI], zi[RI], fxi[RI], fyi[RI], fzi[RI];
+#pragma unroll
+    for (int r = 0; r < RI; ++r) {
+        xi[r] = 0.01 * lane + 0.3 * r; yi[r] = 0.02 * lane; zi[r] = 0.5 + 0.01 * r;
+        fxi[r] = fyi[r] = fzi[r] = 0.0;
+    }
+    sj[warp][0][lane] = 1.5 + 0.011 * lane; sj[warp][1][lane] = 1.0 + 0.02 * lane; sj[warp][2][lane] = 0.7;
+    __syncthreads();
+    double fjx = 0, fjy = 0, fjz = 0, s12 = 0, s6 = 0;
+    unsigned ncut = 0;
+    const long long t0 = clock64();
+    for (int k = 0; k < reps; ++k)
+        sym_chunk<RI, RJ, false, DENSE, false>(sj[warp], xi, yi, zi, fxi, fyi, fzi, fjx, fjy, fjz, s12, s6, ncut, L, 1.0 / L,
+                                           rc2, lane, 0, 1 << 20, 1 << 30);
+    const long long t1 = clock64();
+    double s = fjx + fjy + fjz + s12 + s6;
+#pragma unroll
+    for (int r = 0; r < RI; ++r) s += fxi[r] + fyi[r] + fzi[r];
+    if (s == 1.2345) out[0] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+template <int RI, int RJ>
+static void bench_launch(int dense, int sms, int threads, double *d, long long *dc, int reps, double L, double rc2)
+{
+    if (dense) sym_chunk_bench_kernel<RI, RJ, true><<<sms, threads>>>(d, dc, reps, L, rc2);
+    else sym_chunk_bench_kernel<RI, RJ, false><<<sms, threads>>>(d, dc, reps, L, rc2);
+}
+
+// cycles per 32x(32*ri) tile divided by 32: comparable across rj ("cycles per rotation of one lane")
+int bench_chunk_cycles(int ri, int rj, int dense, int warps_per_cta, double *cycles_per_step)
+{
+    if (warps_per_cta < 1 || warps_per_cta > 32) return set_error(LJMD_ERR_ARG, "warps_per_cta out of range");
+    double *d = nullptr;
+    long long *dc = nullptr;
+    LJMD_CUDA_CHECK(cudaMalloc(&d, 8));
+    LJMD_CUDA_CHECK(cudaMalloc(&dc, 8));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int reps = 64, th = warps_per_cta * 32;
+    const double L = 100.0, rc2 = dense ? 49.0 * 49.0 : 0.01;
+    int ok = 1;
+    for (int pass = 0; pass < 2 && ok; ++pass) {
+        if (ri == 1 && rj == 1) bench_launch<1, 1>(dense, sms, th, d, dc, reps, L, rc2);
+        else if (ri == 2 && rj == 1) bench_launch<2, 1>(dense, sms, th, d, dc, reps, L, rc2);
+        else if (ri == 4 && rj == 1) bench_launch<4, 1>(dense, sms, th, d, dc, reps, L, rc2);
+        else if (ri == 1 && rj == 2) bench_launch<1, 2>(dense, sms, th, d, dc, reps, L, rc2);
+        else if (ri == 2 && rj == 2) bench_launch<2, 2>(dense, sms, th, d, dc, reps, L, rc2);
+        else if (ri == 1 && rj == 4) bench_launch<1, 4>(dense, sms, th, d, dc, reps, L, rc2);
+        else if (ri == 2 && rj == 4) bench_launch<2, 4>(dense, sms, th, d, dc, reps, L, rc2);
+        else if (ri == 4 && rj == 2) bench_launch<4, 2>(dense, sms, th, d, dc, reps, L, rc2);
+        else ok = 0;
+        if (ok) LJMD_CUDA_CHECK(cudaDeviceSynchronize());
+    }
+    long long c = 0;
+    if (ok) LJMD_CUDA_CHECK(cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    cudaFree(dc);
+    if (!ok) return set_error(LJMD_ERR_ARG, "unsupported (ri, rj)");
+    *cycles_per_step = (double)c / (reps * 32.0);
+    return LJMD_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // Planning
 // ------------------------------------------------------------------------------------------
-static int sym_chunks_per_item(int n, int tcta, int R, int sms)
+// Total number of (row, chunk) visits of the triangle.
+static long long sym_total_chunk_visits(int n, int tcta)
 {
-    // total chunk visits over all rows (triangle), then pick the run length so that the launch
-    // has about 3 CTAs per SM (all replicas together) but no run shorter than 2 chunks.
     const int nchunks = (n + 31) / 32;
     const int nrows = (n + tcta - 1) / tcta;
     long long total = 0;
     for (int r = 0; r < nrows; ++r) total += nchunks - (long long)r * tcta / 32;
-    const long long target = std::max<long long>(1, (long long)sms * 3 / std::max(1, R));
-    long long c = (total + target - 1) / target;
-    if (c < 2) c = 2;
-    if (c > nchunks) c = nchunks;
-    return (int)c;
+    return total;
 }
 
 int pairwork_plan(ljmd_ctx *c)
@@ -362,35 +577,84 @@ int pairwork_plan(ljmd_ctx *c)
     } else {
         // geometry: large systems use 4 warps x 4 i-atoms per lane (512-atom rows); small ones
         // 2 x 2 (128-atom rows) so that there are enough work items.
-        if (n >= 2048) { w.ri = 4; w.warps = 4; } else { w.ri = 2; w.warps = 2; }
+        if (n >= 16384) { w.ri = 4; w.warps = 4; } else { w.ri = 2; w.warps = 1; }
+        // fraction of all pairs inside the cutoff sphere: (4 pi / 3) (rc / L)^3
+        const double frac = 4.18879020478639 * c->p.rc * c->p.rc * c->p.rc / c->p.volume;
+        w.dense = frac > 0.15;
+        if (const char *e = getenv("LJMD_SYM_DENSE")) w.dense = atoi(e) != 0;
+
         // tuning overrides (benchmark sweeps only)
         if (const char *e = getenv("LJMD_SYM_RI")) w.ri = atoi(e);
         if (const char *e = getenv("LJMD_SYM_W")) w.warps = atoi(e);
-        if (!((w.ri == 4 && w.warps == 4) || (w.ri == 2 && w.warps == 4) || (w.ri == 4 && w.warps == 2) ||
-              (w.ri == 2 && w.warps == 2) || (w.ri == 1 && w.warps == 4) || (w.ri == 4 && w.warps == 8) ||
-              (w.ri == 2 && w.warps == 8) || (w.ri == 2 && w.warps == 1) || (w.ri == 4 && w.warps == 1)))
-            return set_error(LJMD_ERR_ARG, "unsupported symmetric-kernel geometry RI=%d W=%d", w.ri, w.warps);
+        w.rj = (n >= 16384) ? 1 : 2;
+        if (const char *e = getenv("LJMD_SYM_RJ")) w.rj = atoi(e);
+        // small systems: independent warps (rows of ri*32 atoms) packed into fat CTAs
+        w.indep = (w.warps == 1);
+        w.cta_warps = 16;
+        if (const char *e = getenv("LJMD_SYM_INDEP")) w.indep = atoi(e) != 0;
+        if (w.indep) w.warps = 1;
         const int tcta = w.ri * 32 * w.warps;
         const int nchunks = (n + 31) / 32;
         w.n_rows = (n + tcta - 1) / tcta;
-        w.chunks_per_item = sym_chunks_per_item(n, tcta, c->R, sms);
-        if (const char *e = getenv("LJMD_SYM_CPI")) w.chunks_per_item = std::max(1, std::min(nchunks, atoi(e)));
+        // Every row's chunk run is cut into near-equal items (lengths differ by at most one).
+        //  * independent-warp kernel (small N): one item per warp, all warps resident at once
+        //    (<= 16 warps per SM), so the item length is the smallest k with
+        //    visits / k <= available warps; the kernel time is then k chunk-times for everybody.
+        //  * CTA kernel (large N): about 16 chunks per item, many waves.
+        const long long total = sym_total_chunk_visits(n, tcta);
+        long long target;
+        if (w.indep) {
+            // All 16 warps of every SM stay resident and each takes >= 2 items when there is
+            // enough work (the items a warp runs back to back balance the tail); small systems
+            // get single-chunk items.  Measured per-warp timelines: tools/warp_times.py.
+            const long long slots = std::max<long long>(1, (long long)sms * 16 / std::max(1, c->R));
+            const long long kk = std::max<long long>(1, total / (2 * slots));
+            target = (total + kk - 1) / kk;
+        } else {
+            target = (total + 15) / 16;
+            const long long min_items = (long long)sms * 4 / std::max(1, c->R);
+            if (target < min_items) target = min_items;
+        }
+        if (const char *e = getenv("LJMD_SYM_ITEMS")) target = atoll(e);
+        if (target < 1) target = 1;
         std::vector<int4> items;
+        std::vector<int> row_splits(w.n_rows, 0);
         int max_splits = 0;
         for (int r = 0; r < w.n_rows; ++r) {
             const int first = r * tcta / 32;
-            int split = 0;
-            for (int c0 = first; c0 < nchunks; c0 += w.chunks_per_item, ++split) {
+            const int m = nchunks - first;
+            long long kr = (m * target + total / 2) / total;
+            if (kr < 1) kr = 1;
+            if (kr > m) kr = m;
+            int c0 = first;
+            for (int s = 0; s < (int)kr; ++s) {
+                const int len = m / (int)kr + (s < m % (int)kr ? 1 : 0);
                 int4 it;
-                it.x = r; it.y = c0; it.z = std::min(w.chunks_per_item, nchunks - c0); it.w = split;
+                it.x = r; it.y = c0; it.z = len; it.w = s;
                 items.push_back(it);
+                c0 += len;
             }
-            max_splits = std::max(max_splits, split);
+            row_splits[r] = (int)kr;
+            max_splits = std::max(max_splits, (int)kr);
         }
+        w.chunks_per_item = 0; // unused: per-row split counts live in w.row_splits
+        LJMD_CUDA_CHECK(cudaMalloc(&w.row_splits, sizeof(int) * w.n_rows));
+        LJMD_CUDA_CHECK(cudaMemcpy(w.row_splits, row_splits.data(), sizeof(int) * w.n_rows, cudaMemcpyHostToDevice));
         // heavy items first: full-length runs before the short tails (stable => deterministic)
         std::stable_sort(items.begin(), items.end(), [](const int4 &x, const int4 &y) { return x.z > y.z; });
         w.n_items = (int)items.size();
         w.n_splits = max_splits;
+        w.n_ctas = w.n_items;
+        if (w.indep) {
+            // fat CTAs of 16 independent warps, one CTA per SM when there is enough work
+            int ctas = (w.n_items + 15) / 16;
+            if (c->R == 1) ctas = std::min(ctas, sms);
+            if (const char *e = getenv("LJMD_SYM_CTAS")) ctas = atoi(e);
+            ctas = std::max(1, ctas);
+            w.cta_warps = std::min(16, (w.n_items + ctas - 1) / ctas);
+            if (const char *e = getenv("LJMD_SYM_NW")) w.cta_warps = std::max(1, std::min(16, atoi(e)));
+            w.n_ctas = ctas;
+        }
         LJMD_CUDA_CHECK(cudaMalloc(&w.items, sizeof(int4) * items.size()));
         LJMD_CUDA_CHECK(cudaMemcpy(w.items, items.data(), sizeof(int4) * items.size(), cudaMemcpyHostToDevice));
         const size_t ibytes = sizeof(double) * (size_t)c->R * max_splits * 3 * n;
@@ -400,18 +664,34 @@ int pairwork_plan(ljmd_ctx *c)
         LJMD_CUDA_CHECK(cudaMemsetAsync(w.fpart, 0, ibytes, c->stream));
         LJMD_CUDA_CHECK(cudaMemsetAsync(w.fJ, 0, jbytes, c->stream));
     }
-    const size_t sbytes = sizeof(double) * (size_t)c->R * w.n_items * 3;
+    if (w.variant == 1 && w.indep && getenv("LJMD_SYM_DEBUG")) {
+        LJMD_CUDA_CHECK(cudaMalloc(&w.dbg, sizeof(long long) * 4 * (size_t)w.n_ctas * w.cta_warps));
+        LJMD_CUDA_CHECK(cudaMemset(w.dbg, 0, sizeof(long long) * 4 * (size_t)w.n_ctas * w.cta_warps));
+    }
+    w.n_spart = (w.variant == 1 && w.indep) ? w.n_ctas : w.n_items;
+    const size_t sbytes = sizeof(double) * (size_t)c->R * w.n_spart * 3;
     LJMD_CUDA_CHECK(cudaMalloc(&w.spart, sbytes));
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.spart, 0, sbytes, c->stream));
     return LJMD_OK;
 }
 
-template <int RI, int W>
+template <int RI, int RJ>
+static void launch_symw(ljmd_ctx *c, const SymArgs &a)
+{
+    dim3 grid(c->pw.n_ctas, c->R);
+    const int ni = c->pw.n_items, th = c->pw.cta_warps * 32;
+    if (a.pair_counts) lj_pairs_symw_kernel<RI, RJ, false, true><<<grid, th, 0, c->stream>>>(a, ni);
+    else if (c->pw.dense) lj_pairs_symw_kernel<RI, RJ, true, false><<<grid, th, 0, c->stream>>>(a, ni);
+    else lj_pairs_symw_kernel<RI, RJ, false, false><<<grid, th, 0, c->stream>>>(a, ni);
+}
+
+template <int RI, int RJ, int W>
 static void launch_sym(ljmd_ctx *c, const SymArgs &a)
 {
     dim3 grid(c->pw.n_items, c->R);
-    if (a.pair_counts) lj_pairs_sym_kernel<RI, W, true><<<grid, W * 32, 0, c->stream>>>(a);
-    else lj_pairs_sym_kernel<RI, W, false><<<grid, W * 32, 0, c->stream>>>(a);
+    if (a.pair_counts) lj_pairs_sym_kernel<RI, RJ, W, false, true><<<grid, W * 32, 0, c->stream>>>(a);
+    else if (c->pw.dense) lj_pairs_sym_kernel<RI, RJ, W, true, false><<<grid, W * 32, 0, c->stream>>>(a);
+    else lj_pairs_sym_kernel<RI, RJ, W, false, false><<<grid, W * 32, 0, c->stream>>>(a);
 }
 
 int launch_pairs(ljmd_ctx *c, int buf)
@@ -440,15 +720,24 @@ int launch_pairs(ljmd_ctx *c, int buf)
         a.max_splits = w.n_splits;
         a.n_rows = w.n_rows;
         a.pair_counts = c->fw.pair_counts;
-        if (w.ri == 4 && w.warps == 4) launch_sym<4, 4>(c, a);
-        else if (w.ri == 2 && w.warps == 4) launch_sym<2, 4>(c, a);
-        else if (w.ri == 4 && w.warps == 2) launch_sym<4, 2>(c, a);
-        else if (w.ri == 1 && w.warps == 4) launch_sym<1, 4>(c, a);
-        else if (w.ri == 4 && w.warps == 8) launch_sym<4, 8>(c, a);
-        else if (w.ri == 2 && w.warps == 8) launch_sym<2, 8>(c, a);
-        else if (w.ri == 2 && w.warps == 1) launch_sym<2, 1>(c, a);
-        else if (w.ri == 4 && w.warps == 1) launch_sym<4, 1>(c, a);
-        else launch_sym<2, 2>(c, a);
+        a.dbg = w.dbg;
+        const int key = (w.indep ? 10000 : 0) + w.ri * 1000 + w.rj * 100 + (w.indep ? 0 : w.warps);
+        switch (key) {
+        case 12100: launch_symw<2, 1>(c, a); break;
+        case 12200: launch_symw<2, 2>(c, a); break;
+        case 11400: launch_symw<1, 4>(c, a); break;
+        case 11200: launch_symw<1, 2>(c, a); break;
+        case 14100: launch_symw<4, 1>(c, a); break;
+        case 4104: launch_sym<4, 1, 4>(c, a); break;
+        case 4204: launch_sym<4, 2, 4>(c, a); break;
+        case 2204: launch_sym<2, 2, 4>(c, a); break;
+        case 2104: launch_sym<2, 1, 4>(c, a); break;
+        case 2208: launch_sym<2, 2, 8>(c, a); break;
+        case 4108: launch_sym<4, 1, 8>(c, a); break;
+        default:
+            return set_error(LJMD_ERR_ARG, "unsupported symmetric-kernel geometry RI=%d RJ=%d W=%d indep=%d", w.ri, w.rj,
+                             w.indep ? w.cta_warps : w.warps, (int)w.indep);
+        }
     }
     if (!c->capturing) c->launches++;
     LJMD_CUDA_CHECK(cudaGetLastError());

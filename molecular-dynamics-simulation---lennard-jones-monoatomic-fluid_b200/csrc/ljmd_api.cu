@@ -270,6 +270,8 @@ extern "C" int ljmd_ctx_destroy(ljmd_ctx *c)
     cudaFree(c->pw.spart);
     cudaFree(c->pw.fJ);
     cudaFree(c->pw.items);
+    cudaFree(c->pw.row_splits);
+    cudaFree(c->pw.dbg);
     cudaFree(c->fw.kpart);
     cudaFree(c->fw.counter);
     cudaFree(c->fw.ctl);
@@ -542,6 +544,18 @@ extern "C" int ljmd_ctx_last_step_ms(const ljmd_ctx *c, double *ms)
     return LJMD_OK;
 }
 
+// Tuning aid: copies the per-warp {start, end, smid, items} records of the last independent-warp
+// force launch (needs LJMD_SYM_DEBUG=1 at context creation).  Returns the number of warps.
+extern "C" int ljmd_ctx_debug_warp_times(ljmd_ctx *c, long long *out, int max_warps)
+{
+    if (!c || !c->pw.dbg) return 0;
+    const int nw = c->pw.n_ctas * c->pw.cta_warps;
+    const int m = nw < max_warps ? nw : max_warps;
+    cudaStreamSynchronize(c->stream);
+    if (out && cudaMemcpy(out, c->pw.dbg, sizeof(long long) * 4 * (size_t)m, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return m;
+}
+
 extern "C" int ljmd_ctx_method(const ljmd_ctx *c) { return c ? c->method : -1; }
 extern "C" int ljmd_ctx_cells_per_edge(const ljmd_ctx *c) { return c ? c->cw.nc : 0; }
 extern "C" int64_t ljmd_ctx_launch_count(const ljmd_ctx *c) { return c ? c->launches : 0; }
@@ -586,6 +600,14 @@ extern "C" int ljmd_ctx_pair_counts(ljmd_ctx *c, int64_t *n_candidates, int64_t 
         if (n_in_cutoff) *n_in_cutoff = (int64_t)h[1];
     }
     return LJMD_OK;
+}
+
+extern "C" int ljmd_bench_chunk_cycles(int32_t ri, int32_t rj, int32_t dense, int32_t warps_per_cta, double *cycles_per_step)
+{
+    clear_error();
+    if (!cycles_per_step) return set_error(LJMD_ERR_NULL, "ljmd_bench_chunk_cycles(): NULL argument.");
+    if (ljmd_device_count() == 0) return set_error(LJMD_ERR_CUDA, "ljmd_bench_chunk_cycles(): no CUDA device available.");
+    return bench_chunk_cycles(ri, rj, dense, warps_per_cta, cycles_per_step);
 }
 
 extern "C" int ljmd_measure_fp64_peak(int32_t device, double *tflops)

@@ -68,8 +68,16 @@ struct PairWork {
     int split_len;   // atoms per j split
     // ---- variant 1 ----
     int ri, warps;        // i-atoms per lane, warps per CTA (row = ri*32*warps atoms)
+    int rj;               // rotation offsets per step (pairs per lane-step = ri*rj)
     int n_rows;           // rows of i-atoms
-    int chunks_per_item;  // 32-atom j-chunks per work item
+    int chunks_per_item;  // (unused by the symmetric kernel; kept for the finalize argument block)
+    int *row_splits;      // device [n_rows]: number of work items (= i-side partials) of each row
+    bool dense;           // large in-cutoff fraction: interaction body always executed
+    bool indep;           // independent-warp kernel (rows of ri*32 atoms, fat CTAs of cta_warps)
+    int cta_warps;        // warps per CTA of the independent-warp kernel
+    int n_ctas;           // CTAs per replica of the launch
+    int n_spart;          // scalar partials per replica
+    long long *dbg;       // optional per-warp timestamps of the independent-warp kernel (tuning)
     int4 *items;          // device work-item table
     double *fJ;           // [R][n_rows][3][n] j-side partial forces
     // ---- both ----
@@ -165,6 +173,7 @@ int measure_fp64_peak(int device, double *tflops);
 // ---- lj_allpairs.cu ----------------------------------------------------------------------
 int pairwork_plan(ljmd_ctx *c);
 int launch_pairs(ljmd_ctx *c, int buf); // positions from rbuf[buf]
+int bench_chunk_cycles(int ri, int rj, int dense, int warps_per_cta, double *cycles_per_step);
 
 // ---- lj_cells.cu -------------------------------------------------------------------------
 int cellwork_plan(ljmd_ctx *c);

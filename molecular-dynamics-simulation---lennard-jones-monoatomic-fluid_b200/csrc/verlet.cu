@@ -74,7 +74,8 @@ struct FinArgs {
     int n_splits;
     int sym;                   // symmetric all-pairs kernel: also sum the j-side partials
     const double *fJ;          // [R][n_rows][3][n]
-    int n_rows, tcta, chunks_per_item, nchunks;
+    int n_rows, tcta, nchunks;
+    const int *row_splits;     // [n_rows] i-side partials per row
     const int *perm;           // cells: fpart is in cell-sorted order; perm[i] = sorted slot of atom i
     // scalar partials
     const double *spart;       // [R][n_spart][3]
@@ -111,8 +112,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
             if (a.sym) {
                 const int row = i / a.tcta;
                 nj = row + 1;
-                const int first = row * a.tcta / 32;
-                nsp = (a.nchunks - first + a.chunks_per_item - 1) / a.chunks_per_item;
+                nsp = a.row_splits[row];
             }
             const double *fj = a.sym ? a.fJ + (size_t)rep * a.n_rows * 3 * n : nullptr;
             const double *fp = a.fpart + (size_t)rep * a.n_splits * 3 * n;
@@ -256,7 +256,7 @@ int launch_finalize(ljmd_ctx *c, int mode, int prev, int now, int out)
         a.spart = c->cw.spart;
         a.n_spart = c->cw.nblk_force;
         a.pair_weight = c->cw.pair_weight;
-        a.fJ = nullptr; a.n_rows = 0; a.tcta = 1; a.chunks_per_item = 1; a.nchunks = 0;
+        a.fJ = nullptr; a.n_rows = 0; a.tcta = 1; a.row_splits = nullptr; a.nchunks = 0;
     } else {
         a.fpart = c->pw.fpart;
         a.n_splits = c->pw.n_splits;
@@ -264,10 +264,10 @@ int launch_finalize(ljmd_ctx *c, int mode, int prev, int now, int out)
         a.fJ = c->pw.fJ;
         a.n_rows = c->pw.n_rows;
         a.tcta = c->pw.ri * 32 * c->pw.warps;
-        a.chunks_per_item = c->pw.chunks_per_item;
+        a.row_splits = c->pw.row_splits;
         a.nchunks = (c->sc.n + 31) / 32;
         a.spart = c->pw.spart;
-        a.n_spart = c->pw.n_items;
+        a.n_spart = c->pw.n_spart;
         a.pair_weight = (c->pw.variant == 0) ? 0.5 : 1.0;
     }
     a.kpart = c->fw.kpart;

@@ -16,8 +16,10 @@ ctx.force_timing(True); ctx.step(max(4, nst // 10)); ms, ne = ctx.force_timing(F
 print(json.dumps(dict(step_us=1e3*t, force_us=1e3*ms/ne)))
 ''' % ROOT
 wl, nst = sys.argv[1], sys.argv[2]
-for ri, w in [(4,4),(2,4),(4,1),(2,1),(4,8)]:
-    for cpi in [1,2,4,8] if wl not in ("cfg3_allpairs","dense32k") else [4,16,64]:
-        env = dict(os.environ, LJMD_SYM_RI=str(ri), LJMD_SYM_W=str(w), LJMD_SYM_CPI=str(cpi))
-        r = subprocess.run([sys.executable, "-c", code, wl, nst], env=env, capture_output=True, text=True)
-        print(wl, "RI", ri, "W", w, "CPI", cpi, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:], flush=True)
+# (RI, NW, CTAs, ITEMS)
+cfgs = [(2,8,444,3552),(2,8,444,2664),(2,8,444,4736),(2,8,296,2368),(2,8,296,3552),(2,10,296,2960),(2,20,148,2960),
+        (4,8,296,2368),(4,16,148,2368),(4,8,296,1776)]
+for ri, nw, ctas, items in cfgs:
+    env = dict(os.environ, LJMD_SYM_RI=str(ri), LJMD_SYM_W="1", LJMD_SYM_NW=str(nw), LJMD_SYM_CTAS=str(ctas), LJMD_SYM_ITEMS=str(items))
+    r = subprocess.run([sys.executable, "-c", code, wl, nst], env=env, capture_output=True, text=True)
+    print(wl, "RI", ri, "NW", nw, "CTAS", ctas, "ITEMS", items, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:], flush=True)
