@@ -596,8 +596,9 @@ extern "C" int ljmd_ctx_pair_counts(ljmd_ctx *c, int64_t *n_candidates, int64_t 
         // the full-matrix kernel counts ordered pairs
         if (n_in_cutoff) *n_in_cutoff = (int64_t)(c->pw.variant == 0 ? h[1] / 2 : h[1]);
     } else {
-        if (n_candidates) *n_candidates = (int64_t)h[0];
-        if (n_in_cutoff) *n_in_cutoff = (int64_t)h[1];
+        // the cell kernel visits ordered pairs
+        if (n_candidates) *n_candidates = (int64_t)(h[0] / 2);
+        if (n_in_cutoff) *n_in_cutoff = (int64_t)(h[1] / 2);
     }
     return LJMD_OK;
 }

@@ -106,6 +106,8 @@ struct CellWork {
     int *cell_of_atom;  // [R][n]
     int *cell_start;    // [R][ncells+1]
     int *cell_fill;     // [R][ncells] scratch
+    int *cell_count;    // [R][ncells] histogram
+    int G, nzg, nunits; // cells per z-group, z-groups per column, warp work units
     int *order;         // [R][n] sorted position -> original index
     double *sx, *sy, *sz; // [R][n] positions in cell-sorted order
     double *spart;      // [R][nblk_force][3]

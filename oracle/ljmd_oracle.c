@@ -439,7 +439,7 @@ int32_t orc_cells_per_edge(const orc_params *p)
      * pair by two cells. */
     int32_t nc = (int32_t)floor(p->box_length / p->rc);
     if (nc > 0 && (double)nc * p->rc * (1.0 + 1e-12) > p->box_length) nc -= 1;
-    if (nc > 1024) nc = 1024;
+    if (nc > 128) nc = 128; /* bounded cell table: at most 128^3 cells */
     return nc;
 }
 

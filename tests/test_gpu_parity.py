@@ -235,3 +235,93 @@ def test_error_paths_on_gpu(lj):
 def test_fp64_peak_measurement(lj):
     tf = lj.measure_fp64_peak()
     assert 10.0 < tf < 60.0, tf
+
+
+# ---------------------------------------------------------------------------------------------
+# Cell-list path (no reference counterpart: integer assignments are pinned against the CPU
+# cell oracle, forces against the all-pairs oracle)
+# ---------------------------------------------------------------------------------------------
+def test_cells_golden_n864(lj, O):
+    g = np.load(os.path.join(GOLD, "cells_n864.npz"))
+    p_o = O.params_init(864, float(g["L"]), 1e-3, 2.5, 6)
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    s = [np.ascontiguousarray(a) for a in g["state300"]]
+    with lj.Context(p, method=lj.METHOD_CELLS) as ctx:
+        assert ctx.method == lj.METHOD_CELLS and ctx.cells_per_edge == O.cells_per_edge(p_o) == 4
+        ctx.upload(_state(lj, s))
+        obs = ctx.compute_forces()
+        d = ctx.download(("ax", "ay", "az"))
+        cell, start, order = ctx.download_cells()
+        cand, cut = ctx.pair_counts()
+    # integer assignments: bit-exact
+    assert np.array_equal(cell, g["cell"]) and np.array_equal(start, g["start"]) and np.array_equal(order, g["order"])
+    assert cut == int(g["n_cut"]) and cand >= int(g["n_cand"])
+    for k, name in enumerate(("ax", "ay", "az")):
+        assert rel_err(getattr(d, name), g["acc"][k]) <= TOL
+    for got, want in zip(obs, g["obs"]):
+        assert abs(got - want) <= TOL * abs(want)
+
+
+def test_cells_vs_oracle_32k(lj, O):
+    p_o, st = make_config(O, "cfg3")
+    s = melt(O, p_o, st, 20, cells=True)
+    ax, ay, az, e, d_, dd, ncand, ncut = O.compute_lj_cells(p_o, *s[:3])
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    with lj.Context(p) as ctx:   # AUTO -> cells at N=32000, 13 cells per edge
+        assert ctx.method == lj.METHOD_CELLS and ctx.cells_per_edge == 13
+        ctx.upload(_state(lj, s))
+        obs = ctx.compute_forces()
+        got = ctx.download(("ax", "ay", "az"))
+        cell, start, order = ctx.download_cells()
+        _, cut = ctx.pair_counts()
+    assert cut == ncut
+    assert np.array_equal(cell, O.cell_assign(p_o, *s[:3]))
+    st_o, order_o = O.cell_sort(p_o, cell)
+    assert np.array_equal(start, st_o) and np.array_equal(order, order_o)
+    assert rel_err(got.ax, ax) <= TOL and rel_err(got.ay, ay) <= TOL and rel_err(got.az, az) <= TOL
+    for g_, w_ in zip(obs, (e, d_, dd)):
+        assert abs(g_ - w_) <= TOL * abs(w_)
+    # the all-pairs GPU kernel on the same state agrees too
+    with lj.Context(p, method=lj.METHOD_ALLPAIRS) as ctx:
+        ctx.upload(_state(lj, s))
+        obs2 = ctx.compute_forces()
+        got2 = ctx.download(("ax", "ay", "az"))
+        _, cut2 = ctx.pair_counts()
+    assert cut2 == ncut
+    assert rel_err(got2.ax, ax) <= TOL and np.all(np.abs(obs2 - obs) <= TOL * np.abs(obs))
+
+
+def test_cells_multistep_and_determinism(lj, O):
+    p_o, st = make_config(O, "cfg3")
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    ref = [a.copy() for a in st]
+    for _ in range(5):
+        ref_obs = O.verlet_step(p_o, ref, cells=True)
+    outs = []
+    for _ in range(2):
+        with lj.Context(p, method=lj.METHOD_CELLS) as ctx:
+            ctx.upload(_state(lj, st))
+            obs = ctx.step(5)
+            d = ctx.download()
+            outs.append((obs.copy(), [a.copy() for a in d.arrays()]))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert np.array_equal(a, b)
+    assert np.all(np.abs(outs[0][0] - np.array(ref_obs)) <= 1e-11 * np.abs(np.array(ref_obs)))
+    assert rel_err(outs[0][1][0], ref[0]) <= 1e-11
+
+
+def test_cells_edge_positions(lj, O):
+    """Atoms exactly on cell faces / at x == L (wrapped tiny negatives) bin like the oracle."""
+    g = np.load(os.path.join(GOLD, "cells_n864.npz"))
+    L = float(g["L"])
+    p_o = O.params_init(864, L, 1e-3, 2.5, 6)
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    s = [np.ascontiguousarray(a).copy() for a in g["state300"]]
+    edge = L / 4
+    s[0][:8] = [0.0, L, edge, 2 * edge, 3 * edge, np.nextafter(edge, 0), np.nextafter(L, 0), np.nextafter(2 * edge, 9)]
+    with lj.Context(p, method=lj.METHOD_CELLS) as ctx:
+        ctx.upload(_state(lj, s))
+        ctx.compute_forces()
+        cell, start, order = ctx.download_cells()
+    assert np.array_equal(cell, O.cell_assign(p_o, *s[:3]))
