@@ -184,6 +184,73 @@ def run_reference(args, w, wname):
     print(json.dumps(line), flush=True)
 
 
+def run_sharded(args, w, lj, dist, rank, world, local, n, arrs, p):
+    """Strong scaling of ONE large system (cell list) over the ranks: i-particle-range sharding,
+    NCCL all-gather of the positions every step, observables reduced in rank order."""
+    import importlib
+
+    import torch
+    mg = importlib.import_module(lj.__name__ + ".multi_gpu")
+    dev = torch.device("cuda", local)
+    ctx = lj.Context(p, method=lj.METHOD_CELLS, device=local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.upload(lj.SimState.from_arrays(arrs))
+    ib, ie = mg.shard_range(n, rank, world)
+    ctx.set_shard(ib, ie)
+    ctx.compute_forces()
+    p0, p1, _, _, pobs = ctx.device_ptrs()
+    pos = [mg.torch_view(p0, 3 * n, dev), mg.torch_view(p1, 3 * n, dev)]
+    obs_t = mg.torch_view(pobs, 4, dev)
+    state = {"buf": ctx.shard_begin()}
+
+    def one_step():
+        mg.allgather_positions(pos[state["buf"]], n, rank, world)
+        state["buf"] = ctx.shard_step()
+
+    for _ in range(args.warmup):
+        one_step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        one_step()
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    launches = ctx.launch_count - l0
+    clocks = sampler.finish()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed = float(t.item())
+    obs = mg.reduce_observables(obs_t.clone(), lj.tail_corrections(p))
+    if not np.all(np.isfinite(obs)):
+        raise SystemExit(f"bench.py: non-finite observables {obs}")
+    if rank == 0:
+        line = {
+            "metric": "atom_steps_per_s", "value": n * args.steps / elapsed, "unit": "atom-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "n_atoms": n, "box_length": w["L"], "rc": w["rc"], "dt": w["dt"],
+                       "method": "cells", "multi_gpu": "i-particle ranges, NCCL all-gather of positions every step "
+                       "(3 x %d doubles per rank), observables summed in rank order" % (n // world),
+                       "l2": "state %.0f MB per GPU; positions re-gathered every step" % (96 * n / 1e6)},
+            "roofline": None, "cpu_baseline": None,
+            "e2e": None, "clocks": clocks, "gpu_launches": int(launches * world), "wall_s": wall,
+            "allgather_bytes_per_rank_per_step": 24 * n * (world - 1) // world,
+            "obs_last": [float(x) for x in obs],
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -219,9 +286,12 @@ def main():
     if lj.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
 
-    n, arrs = synthetic_state(w, seed=rank)
+    sharded = world > 1 and w["method"] == "cells"
+    n, arrs = synthetic_state(w, seed=0 if sharded else rank)
     p = lj.init_params(n, w["L"], w["dt"], w["rc"], w["k"])
     method = lj.METHOD_CELLS if w["method"] == "cells" else lj.METHOD_ALLPAIRS
+    if sharded:
+        return run_sharded(args, w, lj, dist, rank, world, local, n, arrs, p)
     ctx = lj.Context(p, method=method, device=local)
     ctx.upload(lj.SimState.from_arrays(arrs))
     ctx.compute_forces()

@@ -160,6 +160,34 @@ int ljmd_ctx_step_series(ljmd_ctx *ctx, int32_t nsteps, double *series);
  * per replica. */
 int ljmd_ctx_kinetic_energy(ljmd_ctx *ctx, double *ekin);
 
+/* ----------------------------------------------------------------------------------------
+ * Multi-GPU plumbing.  One process per GPU; the HOST issues the collectives (torch.distributed /
+ * NCCL) on the same stream.  No reference counterpart (the reference is a serial program).
+ * -------------------------------------------------------------------------------------- */
+/* Run every kernel / copy of this context on the caller's CUDA stream (cudaStream_t); NULL
+ * restores the context's own stream. */
+int ljmd_ctx_set_stream(ljmd_ctx *ctx, void *cuda_stream);
+/* Device addresses: the two position buffers (x array of nreplicas*n doubles, y and z follow),
+ * velocities, accelerations (same layout) and the observables [nreplicas][4].  Any may be NULL. */
+int ljmd_ctx_device_ptrs(ljmd_ctx *ctx, double **pos0, double **pos1, double **vel, double **acc,
+                         double **obs);
+/* i-particle-range sharding of a large system (cell-list method): this context integrates atoms
+ * [i_begin, i_end) and needs all positions from the other ranks each step. */
+int ljmd_ctx_set_shard(ljmd_ctx *ctx, int32_t i_begin, int32_t i_end);
+/* Sharded stepping: shard_begin writes the owned r(t+dt) into position buffer *buf; the host
+ * all-gathers that buffer; shard_step evaluates forces from it, integrates the owned atoms and
+ * returns in *buf the buffer that now holds the owned r(t+2dt) (to be gathered next).  The
+ * observables buffer then holds this rank's share (no tail corrections). */
+int ljmd_ctx_shard_begin(ljmd_ctx *ctx, int32_t *buf_to_gather);
+int ljmd_ctx_shard_step(ljmd_ctx *ctx, int32_t *buf_to_gather);
+int ljmd_ctx_shard_end(ljmd_ctx *ctx);
+/* Tail corrections of lj_potential_energy.f90:205-223 (added once after a cross-rank reduction). */
+int ljmd_tail_corrections(const ljmd_params *params, double *tail_epot, double *tail_d_epot,
+                          double *tail_dd_epot);
+/* Tuning aid: per-warp {start, end, smid, items} clock records of the last independent-warp
+ * all-pairs launch (context created with LJMD_SYM_DEBUG=1); returns the number of warps. */
+int ljmd_ctx_debug_warp_times(ljmd_ctx *ctx, long long *out, int max_warps);
+
 /* Introspection used by tests and benchmarks. */
 int ljmd_ctx_method(const ljmd_ctx *ctx);          /* resolved LJMD_METHOD_* */
 int ljmd_ctx_cells_per_edge(const ljmd_ctx *ctx);  /* 0 for all-pairs */

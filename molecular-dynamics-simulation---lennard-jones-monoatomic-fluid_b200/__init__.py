@@ -85,6 +85,8 @@ ABI_SYMBOLS = [
     "ljmd_ctx_kinetic_energy", "ljmd_ctx_method", "ljmd_ctx_cells_per_edge",
     "ljmd_ctx_launch_count", "ljmd_ctx_last_step_ms", "ljmd_ctx_force_timing", "ljmd_ctx_download_cells",
     "ljmd_ctx_pair_counts", "ljmd_measure_fp64_peak", "ljmd_bench_chunk_cycles",
+    "ljmd_ctx_set_stream", "ljmd_ctx_device_ptrs", "ljmd_ctx_set_shard", "ljmd_ctx_shard_begin",
+    "ljmd_ctx_shard_step", "ljmd_ctx_shard_end", "ljmd_tail_corrections", "ljmd_ctx_debug_warp_times",
 ]
 
 
@@ -200,6 +202,13 @@ def bench_chunk_cycles(ri: int, rj: int, dense: bool, warps_per_cta: int) -> flo
     c = C.c_double()
     _chk(load_library().ljmd_bench_chunk_cycles(ri, rj, 1 if dense else 0, warps_per_cta, C.byref(c)))
     return c.value
+
+
+def tail_corrections(params: SimParams):
+    """lj_potential_energy.f90:205-223: (tail_epot, tail_d_epot, tail_dd_epot)."""
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    _chk(load_library().ljmd_tail_corrections(C.byref(params), C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
 
 
 def measure_fp64_peak(device: int = -1) -> float:
@@ -327,6 +336,33 @@ class Context:
         a, b = C.c_int64(), C.c_int64()
         _chk(self._L.ljmd_ctx_pair_counts(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    # ---- multi-GPU plumbing ------------------------------------------------------------------
+    def set_stream(self, cuda_stream: int) -> None:
+        """Run this context on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        _chk(self._L.ljmd_ctx_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def device_ptrs(self):
+        """(pos0, pos1, vel, acc, obs) device addresses as ints."""
+        ptrs = [C.c_void_p() for _ in range(5)]
+        _chk(self._L.ljmd_ctx_device_ptrs(self._h, *[C.byref(p) for p in ptrs]))
+        return tuple(p.value for p in ptrs)
+
+    def set_shard(self, i_begin: int, i_end: int) -> None:
+        _chk(self._L.ljmd_ctx_set_shard(self._h, int(i_begin), int(i_end)))
+
+    def shard_begin(self) -> int:
+        b = C.c_int32()
+        _chk(self._L.ljmd_ctx_shard_begin(self._h, C.byref(b)))
+        return b.value
+
+    def shard_step(self) -> int:
+        b = C.c_int32()
+        _chk(self._L.ljmd_ctx_shard_step(self._h, C.byref(b)))
+        return b.value
+
+    def shard_end(self) -> None:
+        _chk(self._L.ljmd_ctx_shard_end(self._h))
 
     def download_cells(self):
         nc = self.cells_per_edge

@@ -131,6 +131,8 @@ struct CellForceArgs {
     SimConst sc;
     int nc, G, nzg, nunits;
     const int *start;
+    const int *order;   // sorted slot -> original atom index
+    int own_begin, own_end; // only atoms with original index in [own_begin, own_end) get forces
     const double *sx, *sy, *sz;
     double *fsorted; // [3][n]
     double *spart;   // [gridDim.x][3]
@@ -163,7 +165,9 @@ __global__ void __launch_bounds__(CF_WARPS * 32) cells_force_kernel(CellForceArg
         const bool whole = (zhi - zlo + 1 >= nc);
         for (int i0 = ib; i0 < ie; i0 += 32) {
             const int k = i0 + lane;
-            const bool vi = k < ie;
+            bool vi = k < ie;
+            if (vi) { const int io = a.order[k]; vi = (io >= a.own_begin) && (io < a.own_end); }
+            if (!__any_sync(0xffffffffu, vi)) continue; // nothing owned in this batch (sharded runs)
             const double xi = vi ? a.sx[k] : 0.0, yi = vi ? a.sy[k] : 0.0, zi = vi ? a.sz[k] : 0.0;
             double fx = 0.0, fy = 0.0, fz = 0.0;
             for (int ox = -1; ox <= 1; ++ox) {
@@ -287,6 +291,9 @@ int launch_cells_force(ljmd_ctx *c, int buf)
     a.sc = c->sc;
     a.nc = w.nc; a.G = w.G; a.nzg = w.nzg; a.nunits = w.nunits;
     a.start = w.cell_start;
+    a.order = w.order;
+    a.own_begin = c->sharded ? c->shard_begin : 0;
+    a.own_end = c->sharded ? c->shard_end : n;
     a.sx = w.sx; a.sy = w.sy; a.sz = w.sz;
     a.fsorted = w.fsorted;
     a.spart = w.spart;

@@ -283,7 +283,7 @@ extern "C" int ljmd_ctx_destroy(ljmd_ctx *c)
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_s0) cudaEventDestroy(c->ev_s0);
     if (c->ev_s1) cudaEventDestroy(c->ev_s1);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     cudaGetLastError();
     delete c;
     return LJMD_OK;
@@ -350,6 +350,7 @@ extern "C" int ljmd_ctx_create(const ljmd_params *params, const ljmd_options *op
     DeviceGuard g;
     CREATE_TRY(g.enter(dev));
     CREATE_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = c->stream;
     CREATE_CHECK(cudaEventCreate(&c->ev0));
     CREATE_CHECK(cudaEventCreate(&c->ev1));
     CREATE_CHECK(cudaEventCreate(&c->ev_s0));
@@ -554,6 +555,108 @@ extern "C" int ljmd_ctx_debug_warp_times(ljmd_ctx *c, long long *out, int max_wa
     cudaStreamSynchronize(c->stream);
     if (out && cudaMemcpy(out, c->pw.dbg, sizeof(long long) * 4 * (size_t)m, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return m;
+}
+
+// ==========================================================================================
+// Multi-GPU plumbing (one process per GPU; the host issues the collectives, e.g. torch.distributed)
+// ==========================================================================================
+extern "C" int ljmd_ctx_set_stream(ljmd_ctx *c, void *cuda_stream)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_set_stream(): ctx is NULL.");
+    DeviceGuard g;
+    LJMD_TRY(g.enter(c->device));
+    LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    drop_graphs(c); // graphs were captured on the old stream
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_ctx_device_ptrs(ljmd_ctx *c, double **pos0, double **pos1, double **vel, double **acc,
+                                    double **obs)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_device_ptrs(): ctx is NULL.");
+    if (pos0) *pos0 = c->rbuf[0];
+    if (pos1) *pos1 = c->rbuf[1];
+    if (vel) *vel = c->st.vx;
+    if (acc) *acc = c->st.ax;
+    if (obs) *obs = c->fw.obs;
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_ctx_set_shard(ljmd_ctx *c, int32_t i_begin, int32_t i_end)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_set_shard(): ctx is NULL.");
+    if (c->method != LJMD_METHOD_CELLS || c->R != 1)
+        return set_error(LJMD_ERR_UNSUPPORTED, "ljmd_ctx_set_shard(): i-range sharding needs the cell-list method and one replica.");
+    if (i_begin < 0 || i_end > c->p.n || i_begin >= i_end)
+        return set_error(LJMD_ERR_ARG, "ljmd_ctx_set_shard(): bad range [%d, %d).", i_begin, i_end);
+    drop_graphs(c);
+    c->sharded = !(i_begin == 0 && i_end == c->p.n);
+    c->shard_begin = i_begin;
+    c->shard_end = i_end;
+    c->shard_now = 0;
+    return LJMD_OK;
+}
+
+// Sharded stepping protocol (every rank holds ALL positions, integrates only its own atoms):
+//   ljmd_ctx_compute_forces()            forces on the owned atoms at t=0
+//   ljmd_ctx_shard_begin(&buf)           owned r(t+dt) -> position buffer `buf`
+//   repeat:  [host: all-gather buffer `buf` over the ranks]
+//            ljmd_ctx_shard_step(&buf)   force + finalize for the owned atoms from buffer `buf`;
+//                                        returns the buffer that now holds the owned r(t+2dt)
+// The observables left in the obs buffer are this rank's share without tail corrections.
+extern "C" int ljmd_ctx_shard_begin(ljmd_ctx *c, int32_t *buf_to_gather)
+{
+    clear_error();
+    if (!c || !buf_to_gather) return set_error(LJMD_ERR_NULL, "ljmd_ctx_shard_begin(): NULL argument.");
+    DeviceGuard g;
+    LJMD_TRY(g.enter(c->device));
+    LJMD_TRY(launch_drift(c, 0, 1));
+    c->shard_now = 1;
+    *buf_to_gather = 1;
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_ctx_shard_step(ljmd_ctx *c, int32_t *buf_to_gather)
+{
+    clear_error();
+    if (!c || !buf_to_gather) return set_error(LJMD_ERR_NULL, "ljmd_ctx_shard_step(): NULL argument.");
+    DeviceGuard g;
+    LJMD_TRY(g.enter(c->device));
+    const int now = c->shard_now, prev = 1 - now;
+    LJMD_TRY(enqueue_force(c, now));
+    LJMD_TRY(launch_finalize(c, 1, prev, now, prev));
+    c->shard_now = prev;
+    *buf_to_gather = prev;
+    return LJMD_OK;
+}
+
+// Ends a sharded run: makes position buffer 0 the current one again (the buffer the last force
+// call read holds the complete r(t)).  The caller must NOT have gathered the speculative buffer.
+extern "C" int ljmd_ctx_shard_end(ljmd_ctx *c)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_shard_end(): ctx is NULL.");
+    DeviceGuard g;
+    LJMD_TRY(g.enter(c->device));
+    const int cur = 1 - c->shard_now; // the buffer the last force evaluation used
+    if (cur != 0)
+        LJMD_CUDA_CHECK(cudaMemcpyAsync(c->rbuf[0], c->rbuf[1], sizeof(double) * 3 * c->nR, cudaMemcpyDeviceToDevice, c->stream));
+    LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->shard_now = 0;
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_tail_corrections(const ljmd_params *p, double *tail_epot, double *tail_d_epot, double *tail_dd_epot)
+{
+    clear_error();
+    LJMD_TRY(check_params(p, "ljmd_tail_corrections"));
+    if (!tail_epot || !tail_d_epot || !tail_dd_epot) return set_error(LJMD_ERR_NULL, "ljmd_tail_corrections(): NULL output.");
+    tail_constants(*p, tail_epot, tail_d_epot, tail_dd_epot);
+    return LJMD_OK;
 }
 
 extern "C" int ljmd_ctx_method(const ljmd_ctx *c) { return c ? c->method : -1; }

@@ -139,6 +139,10 @@ struct ljmd_ctx {
                          // state block's rx..rz and always holds the current positions outside
                          // of ljmd_ctx_step; rbuf[1] is the ping-pong partner.
     bool capturing;      // stream capture in progress (launch counters are not advanced)
+    cudaStream_t own_stream; // the stream created with the context (stream may be the caller's)
+    bool sharded;        // multi-GPU i-range sharding: this context integrates [shard_begin, shard_end)
+    int shard_begin, shard_end;
+    int shard_now;       // sharded stepping: index of the position buffer the next force call reads
     ljmd::PairWork pw;
     ljmd::FinalizeWork fw;
     ljmd::CellWork cw;

@@ -34,19 +34,23 @@ __device__ __forceinline__ double drift_wrap(double x, double v, double a, const
 // Velocities are NOT touched here; both half kicks happen in the finalize kernel.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) drift_kernel(SimConst sc, const double *src, double *dst,
-                                                    const double *v, const double *a, size_t total3)
+                                                    const double *v, const double *a, size_t nR, size_t i0,
+                                                    size_t cnt)
 {
-    // src/dst/v/a are the x arrays; y and z follow at stride nR => treat as one array of 3*nR
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total3) return;
+    // src/dst/v/a are the x arrays; y and z follow at stride nR.  blockIdx.y = component.
+    // Only atoms [i0, i0+cnt) are advanced (the whole system unless the context is sharded).
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    const size_t i = (size_t)blockIdx.y * nR + i0 + t;
     dst[i] = drift_wrap(src[i], v[i], a[i], sc);
 }
 
 int launch_drift(ljmd_ctx *c, int from, int to)
 {
-    const size_t total3 = 3 * c->nR;
-    const unsigned grid = (unsigned)((total3 + 255) / 256);
-    drift_kernel<<<grid, 256, 0, c->stream>>>(c->sc, c->rbuf[from], c->rbuf[to], c->st.vx, c->st.ax, total3);
+    const size_t i0 = c->sharded ? (size_t)c->shard_begin : 0;
+    const size_t cnt = c->sharded ? (size_t)(c->shard_end - c->shard_begin) : c->nR;
+    dim3 grid((unsigned)((cnt + 255) / 256), 3);
+    drift_kernel<<<grid, 256, 0, c->stream>>>(c->sc, c->rbuf[from], c->rbuf[to], c->st.vx, c->st.ax, c->nR, i0, cnt);
     if (!c->capturing) c->launches++;
     LJMD_CUDA_CHECK(cudaGetLastError());
     return LJMD_OK;
@@ -77,6 +81,7 @@ struct FinArgs {
     int n_rows, tcta, nchunks;
     const int *row_splits;     // [n_rows] i-side partials per row
     const int *perm;           // cells: fpart is in cell-sorted order; perm[i] = sorted slot of atom i
+    int i_begin, i_end;        // atoms handled by this launch (the whole system unless sharded)
     // scalar partials
     const double *spart;       // [R][n_spart][3]
     int n_spart;
@@ -98,10 +103,11 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
     const int rep = blockIdx.y;
     const size_t off = (size_t)rep * n;
     const int la = threadIdx.x % APB, g = threadIdx.x / APB;
-    const int i = blockIdx.x * APB + la;
+    const int i = a.i_begin + blockIdx.x * APB + la;
+    const int i_end = a.i_end;
 
     double fx = 0.0, fy = 0.0, fz = 0.0;
-    if (i < n) {
+    if (i < i_end) {
         if (a.perm) {
             const int k = a.perm[off + i];
             const double *fp = a.fpart + (size_t)rep * 3 * n;
@@ -137,7 +143,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
     }
 
     double k[3] = {0.0, 0.0, 0.0};
-    if (i < n && g == 0) {
+    if (i < i_end && g == 0) {
         const size_t ix = off + i, iy = ix + a.nR, iz = iy + a.nR;
         const double axn = 24.0 * fx, ayn = 24.0 * fy, azn = 24.0 * fz; // lj_potential_energy.f90:189-191
         double vx = a.vx[ix], vy = a.vx[iy], vz = a.vx[iz];
@@ -239,6 +245,9 @@ int launch_finalize(ljmd_ctx *c, int mode, int prev, int now, int out)
 {
     FinArgs a;
     a.sc = c->sc;
+    a.i_begin = c->sharded ? c->shard_begin : 0;
+    a.i_end = c->sharded ? c->shard_end : c->sc.n;
+    if (c->sharded) { a.sc.tail_u = 0.0; a.sc.tail_du = 0.0; a.sc.tail_ddu = 0.0; } // added once, after the reduction
     a.nR = c->nR;
     a.vx = c->st.vx;
     a.ax = c->st.ax;
@@ -274,7 +283,8 @@ int launch_finalize(ljmd_ctx *c, int mode, int prev, int now, int out)
     a.counter = c->fw.counter;
     a.obs = c->fw.obs;
     a.ctl = c->fw.ctl;
-    dim3 grid(c->fw.nblk, c->R);
+    const int apb = 256 / c->fw.groups;
+    dim3 grid(c->sharded ? (a.i_end - a.i_begin + apb - 1) / apb : c->fw.nblk, c->R);
     if (c->fw.groups == 8) finalize_kernel<8><<<grid, 256, 0, c->stream>>>(a);
     else finalize_kernel<1><<<grid, 256, 0, c->stream>>>(a);
     if (!c->capturing) c->launches++;

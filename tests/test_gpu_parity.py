@@ -325,3 +325,65 @@ def test_cells_edge_positions(lj, O):
         ctx.compute_forces()
         cell, start, order = ctx.download_cells()
     assert np.array_equal(cell, O.cell_assign(p_o, *s[:3]))
+
+
+# ---------------------------------------------------------------------------------------------
+# i-range sharding, two "ranks" emulated as two contexts on one GPU (the exchange is done by
+# hand; the NCCL path itself is exercised by bench.py --gpus N and tests/test_multi_gpu_host.py)
+# ---------------------------------------------------------------------------------------------
+def test_sharded_contexts_match_single(lj, O):
+    import importlib
+
+    import torch
+    mg = importlib.import_module(lj.__name__ + ".multi_gpu")
+    g = np.load(os.path.join(GOLD, "cells_n864.npz"))
+    n = 864
+    p_o = O.params_init(n, float(g["L"]), 1e-3, 2.5, 6)
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    s = [np.ascontiguousarray(a) for a in g["state300"]]
+    nsteps, world = 6, 2
+    dev = torch.device("cuda", 0)
+    with lj.Context(p, method=lj.METHOD_CELLS) as ref:
+        ref.upload(_state(lj, s))
+        ref.compute_forces()
+        ref_obs = ref.step(nsteps)
+        ref_state = ref.download()
+    ctxs = [lj.Context(p, method=lj.METHOD_CELLS) for _ in range(world)]
+    try:
+        views, bufs = [], []
+        for r, c in enumerate(ctxs):
+            c.upload(_state(lj, s))
+            c.set_shard(*mg.shard_range(n, r, world))
+            c.compute_forces()
+            p0, p1, _, _, pobs = c.device_ptrs()
+            views.append(([mg.torch_view(p0, 3 * n, dev), mg.torch_view(p1, 3 * n, dev)], mg.torch_view(pobs, 4, dev)))
+            bufs.append(c.shard_begin())
+        for _ in range(nsteps):
+            torch.cuda.synchronize()
+            b = bufs[0]
+            assert all(x == b for x in bufs)
+            # "all-gather": every context receives the owned ranges of the others
+            for r in range(world):
+                lo, hi = mg.shard_range(n, r, world)
+                for q in range(world):
+                    if q != r:
+                        for comp in range(3):
+                            views[q][0][b][comp * n + lo:comp * n + hi] = views[r][0][b][comp * n + lo:comp * n + hi]
+            torch.cuda.synchronize()
+            bufs = [c.shard_step() for c in ctxs]
+        torch.cuda.synchronize()
+        parts = [v[1].cpu().numpy().copy() for v in views]
+        tails = lj.tail_corrections(p)
+        tot = parts[0] + parts[1]
+        tot[0] += tails[0]; tot[2] += tails[1]; tot[3] += tails[2]
+        assert np.all(np.abs(tot - ref_obs) <= 1e-13 * np.abs(ref_obs))
+        for r, c in enumerate(ctxs):
+            c.shard_end()
+            d = c.download()
+            lo, hi = mg.shard_range(n, r, world)
+            assert np.array_equal(d.rx, ref_state.rx)               # all positions, bitwise
+            assert np.array_equal(d.vx[lo:hi], ref_state.vx[lo:hi])  # owned velocities / forces
+            assert np.array_equal(d.az[lo:hi], ref_state.az[lo:hi])
+    finally:
+        for c in ctxs:
+            c.close()
