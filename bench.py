@@ -46,6 +46,8 @@ WORKLOADS = {
     "cfg3_cells": dict(k=20, L=34.19951893353394, rc=2.5, dt=1e-3, method="cells", T=1.0),
     "dense32k": dict(k=20, L=40.0, rc=19.6, dt=1e-4, method="allpairs", T=1.416),  # tuning only
     "cfg4_cells": dict(k=64, L=109.4384605873086, rc=2.5, dt=1e-3, method="cells", T=1.0),
+    "cfg3_nlist": dict(k=20, L=34.19951893353394, rc=2.5, dt=1e-3, method="nlist", T=1.0),
+    "cfg4_nlist": dict(k=64, L=109.4384605873086, rc=2.5, dt=1e-3, method="nlist", T=1.0),
 }
 
 
@@ -143,7 +145,7 @@ def time_oracle(w, arrs, budget_s, variant="O2", max_steps=None):
     n = 4 * w["k"] ** 3
     p = O.params_init(n, w["L"], w["dt"], w["rc"], w["k"])
     st = [a.copy() for a in arrs]
-    cells = w["method"] == "cells"
+    cells = w["method"] in ("cells", "nlist")
     if cells:
         O.compute_lj_cells(p, *st[:3])
     O.verlet_step(p, st, variant=variant, cells=cells)  # warm-up (also gives a(t))
@@ -173,7 +175,7 @@ def run_reference(args, w, wname):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": wname, "n_atoms": n, "box_length": w["L"], "rc": w["rc"],
-                   "dt": w["dt"], "method": "cells(cpu)" if w["method"] == "cells" else "allpairs"},
+                   "dt": w["dt"], "method": "cells(cpu)" if w["method"] in ("cells", "nlist") else "allpairs"},
         "cpu_baseline": {"value": val, "unit": "atom-steps/s", "cores": 1, "kind": "port",
                          "sample": f"{steps} verlet_step calls of the C restatement of the reference "
                                    f"(gcc -O2 -ffp-contract=off = shipped gfortran flags), 1 thread "
@@ -289,7 +291,7 @@ def main():
     sharded = world > 1 and w["method"] == "cells"
     n, arrs = synthetic_state(w, seed=0 if sharded else rank)
     p = lj.init_params(n, w["L"], w["dt"], w["rc"], w["k"])
-    method = lj.METHOD_CELLS if w["method"] == "cells" else lj.METHOD_ALLPAIRS
+    method = {"cells": lj.METHOD_CELLS, "nlist": lj.METHOD_NLIST}.get(w["method"], lj.METHOD_ALLPAIRS)
     if sharded:
         return run_sharded(args, w, lj, dist, rank, world, local, n, arrs, p)
     ctx = lj.Context(p, method=method, device=local)

@@ -72,9 +72,13 @@ enum {
 
 /* Force method of a context. */
 enum {
-    LJMD_METHOD_AUTO = 0,     /* all-pairs unless floor(L/rc) >= 4 and N >= 16384 */
+    LJMD_METHOD_AUTO = 0,     /* all-pairs unless floor(L/(rc+skin)) >= 4 and N >= 8192 (then NLIST) */
     LJMD_METHOD_ALLPAIRS = 1, /* O(N^2), the reference's algorithm */
-    LJMD_METHOD_CELLS = 2     /* counting-sort cell list + 27-cell stencil (no reference counterpart) */
+    LJMD_METHOD_CELLS = 2,    /* counting-sort cell list + 27-cell stencil every step */
+    LJMD_METHOD_NLIST = 3     /* counting-sort cells + Verlet neighbour list with skin, one fused
+                                 kernel per step, state kept in cell-sorted order on the device
+                                 (CELLS and NLIST have no reference counterpart: the reference is
+                                 all-pairs only, lj_potential_energy.f90:109-183) */
 };
 
 /* Context flags. */
@@ -205,6 +209,15 @@ int ljmd_ctx_force_timing(ljmd_ctx *ctx, int32_t enable, double *ms_total, int64
  * order[n] (original index of the k-th atom in cell-sorted order).  Any pointer may be NULL. */
 int ljmd_ctx_download_cells(ljmd_ctx *ctx, int32_t *cell_of_atom, int32_t *cell_start,
                             int32_t *order);
+/* Neighbour-list introspection (LJMD_METHOD_NLIST only).  Any pointer may be NULL.
+ * skin: list radius is rc + skin; capacity: list slots per atom; rebuilds: list builds so far;
+ * entries: total (ordered) list entries of the current list. */
+int ljmd_ctx_nlist_info(ljmd_ctx *ctx, double *skin, int32_t *cells_per_edge, int32_t *capacity,
+                        int64_t *rebuilds, int64_t *entries);
+/* Neighbour list of the last build in ORIGINAL atom numbering: counts[n]; the neighbours of atom i
+ * (ascending) at nbr[i*cap .. i*cap + counts[i]).  j is listed for i iff the minimum-image r_ij^2,
+ * computed in the reference's operation order (lj_potential_energy.f90:119-129), is < (rc+skin)^2. */
+int ljmd_ctx_download_nlist(ljmd_ctx *ctx, int32_t *counts, int32_t *nbr, int32_t cap);
 /* Unordered candidate pairs distance-tested / in-cutoff pairs of the last force evaluation. */
 int ljmd_ctx_pair_counts(ljmd_ctx *ctx, int64_t *n_candidates, int64_t *n_in_cutoff);
 

@@ -28,7 +28,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libljmd.so")
 
-METHOD_AUTO, METHOD_ALLPAIRS, METHOD_CELLS = 0, 1, 2
+METHOD_AUTO, METHOD_ALLPAIRS, METHOD_CELLS, METHOD_NLIST = 0, 1, 2, 3
 FLAG_TRACK_UNWRAPPED = 1
 
 ERR_NAMES = {
@@ -87,6 +87,7 @@ ABI_SYMBOLS = [
     "ljmd_ctx_pair_counts", "ljmd_measure_fp64_peak", "ljmd_bench_chunk_cycles",
     "ljmd_ctx_set_stream", "ljmd_ctx_device_ptrs", "ljmd_ctx_set_shard", "ljmd_ctx_shard_begin",
     "ljmd_ctx_shard_step", "ljmd_ctx_shard_end", "ljmd_tail_corrections", "ljmd_ctx_debug_warp_times",
+    "ljmd_ctx_nlist_info", "ljmd_ctx_download_nlist",
 ]
 
 
@@ -363,6 +364,25 @@ class Context:
 
     def shard_end(self) -> None:
         _chk(self._L.ljmd_ctx_shard_end(self._h))
+
+    def nlist_info(self):
+        """(skin, cells_per_edge, capacity, rebuilds, entries) of the neighbour-list path."""
+        skin, nc, cap = C.c_double(), C.c_int32(), C.c_int32()
+        reb, ent = C.c_int64(), C.c_int64()
+        _chk(self._L.ljmd_ctx_nlist_info(self._h, C.byref(skin), C.byref(nc), C.byref(cap),
+                                         C.byref(reb), C.byref(ent)))
+        return {"skin": skin.value, "cells_per_edge": nc.value, "capacity": cap.value,
+                "rebuilds": reb.value, "entries": ent.value}
+
+    def download_nlist(self):
+        """Neighbour list of the last build in original numbering: (counts[n], nbr[n, cap])."""
+        cap = self.nlist_info()["capacity"]
+        n = self.params.n
+        counts = np.zeros(n, dtype=np.int32)
+        nbr = np.full((n, cap), -1, dtype=np.int32)
+        _chk(self._L.ljmd_ctx_download_nlist(self._h, counts.ctypes.data_as(_IP),
+                                             nbr.ctypes.data_as(_IP), cap))
+        return counts, nbr
 
     def download_cells(self):
         nc = self.cells_per_edge

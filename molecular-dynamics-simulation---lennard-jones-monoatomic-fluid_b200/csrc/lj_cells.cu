@@ -39,20 +39,23 @@ int cells_per_edge_host(const ljmd_params &p)
 }
 
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int cell_coord(double x, double scale, int nc)
+__device__ __forceinline__ int cell_coord(double x, double scale, int nc, double L, double invL)
 {
+    // out-of-box coordinates (unwrapped input, geometry_pbc.f90:18-19) are wrapped for binning
+    if (x < 0.0 || x > L) x = x - L * floor(x * invL);
     int c = (int)floor(x * scale); // one rounding, as on the host
     c = max(c, 0);
     return min(c, nc - 1);         // wrapped x may equal L exactly (geometry_pbc.f90:53-57)
 }
 
-__global__ void __launch_bounds__(256) cell_count_kernel(int n, int nc, double scale, const double *rx,
-                                                         const double *ry, const double *rz, int *cell_of_atom,
-                                                         int *count)
+__global__ void __launch_bounds__(256) cell_count_kernel(int n, int nc, double scale, double L, double invL,
+                                                         const double *rx, const double *ry, const double *rz,
+                                                         int *cell_of_atom, int *count)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int cx = cell_coord(rx[i], scale, nc), cy = cell_coord(ry[i], scale, nc), cz = cell_coord(rz[i], scale, nc);
+    const int cx = cell_coord(rx[i], scale, nc, L, invL), cy = cell_coord(ry[i], scale, nc, L, invL),
+              cz = cell_coord(rz[i], scale, nc, L, invL);
     const int c = (cx * nc + cy) * nc + cz;
     cell_of_atom[i] = c;
     atomicAdd(&count[c], 1);
@@ -282,7 +285,8 @@ int launch_cells_force(ljmd_ctx *c, int buf)
     const int n = c->sc.n;
     const double *px = c->rbuf[buf], *py = px + c->nR, *pz = py + c->nR;
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (size_t)w.ncells, c->stream));
-    cell_count_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, w.nc, w.scale, px, py, pz, w.cell_of_atom, w.cell_count);
+    cell_count_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, w.nc, w.scale, c->sc.L, c->sc.invL, px, py, pz, w.cell_of_atom,
+                                                               w.cell_count);
     cell_scan_kernel<<<1, 1024, 0, c->stream>>>(w.ncells, w.cell_count, w.cell_start, w.cell_fill);
     cell_fill_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, w.cell_of_atom, w.cell_start, w.cell_fill, w.order);
     cell_sort_kernel<<<(w.ncells + 127) / 128, 128, 0, c->stream>>>(w.ncells, n, w.cell_start, w.order, w.slot_of_atom,
@@ -312,11 +316,16 @@ extern "C" int ljmd_ctx_download_cells(ljmd_ctx *c, int32_t *cell_of_atom, int32
     using namespace ljmd;
     clear_error();
     if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_download_cells(): ctx is NULL.");
-    if (c->method != LJMD_METHOD_CELLS)
+    if (c->method != LJMD_METHOD_CELLS && c->method != LJMD_METHOD_NLIST)
         return set_error(LJMD_ERR_ARG, "ljmd_ctx_download_cells(): context does not use the cell list.");
     int prev = 0;
     LJMD_CUDA_CHECK(cudaGetDevice(&prev));
     if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
+    if (c->method == LJMD_METHOD_NLIST) {
+        const int rc = nlist_download_cells(c, cell_of_atom, cell_start, order);
+        if (prev != c->device) cudaSetDevice(prev);
+        return rc;
+    }
     const CellWork &w = c->cw;
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e == cudaSuccess && cell_of_atom)

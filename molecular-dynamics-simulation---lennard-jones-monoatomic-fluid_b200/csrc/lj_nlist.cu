@@ -1,0 +1,945 @@
+// lj_nlist.cu -- large-N path: counting-sort cells + Verlet neighbour list + ONE fused kernel per
+// velocity-Verlet step (force, both half kicks, E_kin, next drift + wrap, unwrapped update,
+// skin check, deterministic reductions).
+//
+// No reference counterpart: the reference is all-pairs only
+// (/root/reference/scripts/physics/lj_potential_energy.f90:109-183).  The per-pair arithmetic,
+// the minimum image (physics/geometry_pbc.f90:86), the strict cutoff r2 < rc2 evaluated on r2 in
+// the reference's operation order (:129,:132) and the Verlet arithmetic (physics/verlet.f90:58-95)
+// are the same as in the all-pairs path, so the set of interacting pairs is identical to the
+// reference's and every per-pair term agrees to <= 1 ulp.
+//
+// Design
+//   * The resident state lives in CELL-SORTED order (slot k holds original atom orig[k]); it is
+//     re-sorted only when the list is rebuilt.  Contiguous slot ranges are spatial slabs.
+//   * Rebuild (only when some atom moved more than skin/2 since the last build, decided on the
+//     device, no host round trip): cell id of every atom -> histogram (integer atomics) ->
+//     exclusive scan -> scatter -> per-cell sort by ORIGINAL index (= the stable counting sort,
+//     bit-exact against the CPU definition) -> permute all state arrays -> full neighbour list
+//     {j : |r_ij|_mic^2 < (rc+skin)^2}, stored transposed (entry m of slot i at nbr[m*stride+i])
+//     so that a warp reads 128 contiguous bytes per entry.
+//   * Step kernel: one thread per atom walks its list (ordered pairs: every thread accumulates
+//     only its own atom => no atomics, fixed summation order, bit-reproducible), gathers r_j from
+//     L1/L2, and finishes the velocity-Verlet step for its atom in the epilogue.  Warps whose atoms
+//     all sit in interior cells skip the minimum image (dx - L*0 = dx exactly); boundary warps use
+//     the rint() form.  The last CTA reduces the scalar partials in a fixed order.
+//   * Skin criterion (exact): a pair absent from the list had r > rc+skin at build time; while no
+//     atom has moved more than skin/2 it is still beyond rc.  The epilogue measures the displacement
+//     of the positions it just produced against the build positions.
+#include <algorithm>
+#include <cmath>
+#include <cstddef>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "ljmd_internal.h"
+#include "lj_pair.cuh"
+#include "reduce.cuh"
+
+namespace ljmd {
+
+constexpr int NL_BS = 128; // threads per CTA of the per-atom kernels
+
+// Kernel argument block (passed by value).
+struct NlArgs {
+    SimConst sc;
+    int nc, ncells;
+    double scale;      // nc / L
+    double rl2;        // (rc + skin)^2
+    double half_skin2; // (skin/2)^2
+    int maxnb;
+    size_t stride;
+    double *rb[2];     // position buffers: x array; y, z follow at +n, +2n
+    double *v, *a;     // x arrays; y, z at +n, +2n
+    double *ru;        // unwrapped x array or nullptr
+    double *r0;        // [3][n] positions at the last list build
+    double *alt;       // [narr][n] permutation scratch
+    double *arr[15];   // the state arrays that are permuted at a rebuild
+    int narr;
+    int *cell_of_slot, *cell_count, *cell_start, *cell_cursor;
+    unsigned long long *keys;
+    int *orig, *orig_alt, *slot_of_orig;
+    unsigned char *interior;
+    int *nb_cnt, *nbr;
+    NlCtl *ctl;
+    StepCtl *sctl;
+    double *spart; // [nblk][5]
+    int nblk;
+    double *obs;   // [4]
+    int eval_sel;  // rebuild kernels: 0 = the list is for rb[cur], 1 = for rb[1-cur]
+    unsigned long long *pair_counts;
+};
+
+// 1/x to <= 1 ulp (see lj_allpairs.cu).
+__device__ __forceinline__ double nl_rcp(double x)
+{
+    double y0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double e = fma(-x, y0, 1.0);
+    const double t = fma(e, e, e);
+    return fma(y0, t, y0);
+}
+
+// Cell coordinate of x.  In-box x (0 <= x <= L, what wrap_positions produces,
+// geometry_pbc.f90:53-57) bins as floor(x*scale) clamped to [0, nc-1]; out-of-box x (the force
+// routine also accepts unwrapped input, geometry_pbc.f90:18-19) is wrapped for binning only.
+__device__ __forceinline__ int nl_cell_coord(double x, double L, double invL, double scale, int nc, bool &outside)
+{
+    if (x < 0.0 || x > L) { x = x - L * floor(x * invL); outside = true; }
+    int c = (int)floor(x * scale);
+    c = max(c, 0);
+    return min(c, nc - 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// Rebuild sequence.  Every kernel returns at once unless ctl->need_rebuild is set.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nl_bin_kernel(NlArgs a)
+{
+    if (!a.ctl->need_rebuild) return;
+    const int n = a.sc.n;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double *px = a.rb[a.ctl->cur ^ a.eval_sel];
+    bool outside = false;
+    const int cx = nl_cell_coord(px[k], a.sc.L, a.sc.invL, a.scale, a.nc, outside);
+    const int cy = nl_cell_coord(px[(size_t)n + k], a.sc.L, a.sc.invL, a.scale, a.nc, outside);
+    const int cz = nl_cell_coord(px[2 * (size_t)n + k], a.sc.L, a.sc.invL, a.scale, a.nc, outside);
+    const int c = (cx * a.nc + cy) * a.nc + cz;
+    a.cell_of_slot[k] = c;
+    atomicAdd(&a.cell_count[c], 1); // integer histogram: order-independent
+    if (outside) a.ctl->unwrapped = 1;
+}
+
+// Exclusive scan, one CTA: every thread sums a contiguous run of cells, the run totals are scanned
+// in shared memory, then every thread writes its run.  Also re-arms the histogram and the cursors.
+__global__ void __launch_bounds__(1024) nl_scan_kernel(NlArgs a)
+{
+    if (!a.ctl->need_rebuild) return;
+    __shared__ int wsum[32];
+    const int ncells = a.ncells;
+    const int per = (ncells + 1023) / 1024;
+    const int b = threadIdx.x * per, e = min(ncells, b + per);
+    int s = 0;
+    for (int c = b; c < e; ++c) s += a.cell_count[c];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int x = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int w = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        wsum[lane] = w;
+    }
+    __syncthreads();
+    int run = (warp > 0 ? wsum[warp - 1] : 0) + x - s; // exclusive prefix of this thread's run
+    for (int c = b; c < e; ++c) {
+        const int v = a.cell_count[c];
+        a.cell_start[c] = run;
+        a.cell_cursor[c] = 0;
+        a.cell_count[c] = 0;
+        run += v;
+    }
+    if (threadIdx.x == 1023) a.cell_start[ncells] = wsum[31];
+}
+
+__global__ void __launch_bounds__(256) nl_fill_kernel(NlArgs a)
+{
+    if (!a.ctl->need_rebuild) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.sc.n) return;
+    const int c = a.cell_of_slot[k];
+    const int pos = a.cell_start[c] + atomicAdd(&a.cell_cursor[c], 1);
+    a.keys[pos] = ((unsigned long long)(unsigned)a.orig[k] << 32) | (unsigned)k;
+}
+
+// One thread per cell: sort the (short) segment by original index => stable counting sort.
+__global__ void __launch_bounds__(128) nl_sortcell_kernel(NlArgs a)
+{
+    if (!a.ctl->need_rebuild) return;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.ncells) return;
+    const int b = a.cell_start[c], e = a.cell_start[c + 1];
+    for (int k = b + 1; k < e; ++k) {
+        const unsigned long long v = a.keys[k];
+        int m = k - 1;
+        while (m >= b && a.keys[m] > v) { a.keys[m + 1] = a.keys[m]; --m; }
+        a.keys[m + 1] = v;
+    }
+}
+
+// New slot k takes the atom that sat in old slot (keys[k] & 0xffffffff).
+__global__ void __launch_bounds__(256) nl_permute_kernel(NlArgs a)
+{
+    if (!a.ctl->need_rebuild) return;
+    const int n = a.sc.n;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const unsigned long long key = a.keys[k];
+    const int old = (int)(key & 0xffffffffu), o = (int)(key >> 32);
+    for (int q = 0; q < a.narr; ++q) a.alt[(size_t)q * n + k] = a.arr[q][old];
+    a.orig_alt[k] = o;
+    a.slot_of_orig[o] = k;
+}
+
+__global__ void __launch_bounds__(256) nl_copyback_kernel(NlArgs a)
+{
+    if (!a.ctl->need_rebuild) return;
+    const int n = a.sc.n;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    for (int q = 0; q < a.narr; ++q) a.arr[q][k] = a.alt[(size_t)q * n + k];
+    a.orig[k] = a.orig_alt[k];
+}
+
+// Full neighbour list of every slot from the 27-cell stencil (9 z-strips, contiguous in the
+// sorted order).  Membership is decided on r2 computed exactly like the reference computes it.
+__global__ void __launch_bounds__(NL_BS) nl_build_kernel(NlArgs a)
+{
+    if (!a.ctl->need_rebuild) return;
+    const int n = a.sc.n, nc = a.nc;
+    const int i = blockIdx.x * NL_BS + threadIdx.x;
+    if (i < n) {
+        const double *px = a.rb[a.ctl->cur ^ a.eval_sel], *py = px + n, *pz = py + n;
+        const double L = a.sc.L, invL = a.sc.invL, rl2 = a.rl2;
+        const double xi = px[i], yi = py[i], zi = pz[i];
+        bool outside = false;
+        const int cx = nl_cell_coord(xi, L, invL, a.scale, nc, outside);
+        const int cy = nl_cell_coord(yi, L, invL, a.scale, nc, outside);
+        const int cz = nl_cell_coord(zi, L, invL, a.scale, nc, outside);
+        const int zlo = cz - 1, zhi = cz + 1;
+        const bool whole = (nc <= 3);
+        int cnt = 0;
+        int *nb = a.nbr + i;
+        for (int ox = -1; ox <= 1; ++ox) {
+            const int nx = (cx + ox + nc) % nc;
+            for (int oy = -1; oy <= 1; ++oy) {
+                const int ny = (cy + oy + nc) % nc;
+                const int base = (nx * nc + ny) * nc;
+                int sb[2], se[2], npieces;
+                if (whole) {
+                    sb[0] = a.cell_start[base]; se[0] = a.cell_start[base + nc]; npieces = 1;
+                } else if (zlo < 0) {
+                    sb[0] = a.cell_start[base + nc - 1]; se[0] = a.cell_start[base + nc];
+                    sb[1] = a.cell_start[base]; se[1] = a.cell_start[base + zhi + 1]; npieces = 2;
+                } else if (zhi >= nc) {
+                    sb[0] = a.cell_start[base + zlo]; se[0] = a.cell_start[base + nc];
+                    sb[1] = a.cell_start[base]; se[1] = a.cell_start[base + 1]; npieces = 2;
+                } else {
+                    sb[0] = a.cell_start[base + zlo]; se[0] = a.cell_start[base + zhi + 1]; npieces = 1;
+                }
+                for (int pc = 0; pc < npieces; ++pc) {
+                    for (int j = sb[pc]; j < se[pc]; ++j) {
+                        const double dx = mic(xi - px[j], L, invL);
+                        const double dy = mic(yi - py[j], L, invL);
+                        const double dz = mic(zi - pz[j], L, invL);
+                        const double r2 = dist2(dx, dy, dz);
+                        if (r2 < rl2 && j != i) {
+                            if (cnt < a.maxnb) nb[(size_t)cnt * a.stride] = j;
+                            ++cnt;
+                        }
+                    }
+                }
+            }
+        }
+        a.nb_cnt[i] = min(cnt, a.maxnb);
+        if (cnt > a.maxnb) atomicMax(&a.ctl->overflow, cnt);
+        a.r0[i] = xi; a.r0[(size_t)n + i] = yi; a.r0[2 * (size_t)n + i] = zi;
+        const bool inter = cx >= 1 && cx <= nc - 2 && cy >= 1 && cy <= nc - 2 && cz >= 1 && cz <= nc - 2;
+        a.interior[i] = inter ? 1 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned t = atomicAdd(&a.ctl->ticket_build, 1u);
+        if (t == gridDim.x - 1) { // every CTA has passed its need_rebuild test
+            a.ctl->ticket_build = 0;
+            a.ctl->maxd2_bits = 0ull;
+            a.ctl->rebuilds += 1;
+            __threadfence();
+            a.ctl->need_rebuild = 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-pair body, branch-free: an entry outside the cutoff contributes exact zeros.
+// ------------------------------------------------------------------------------------------
+template <bool MIC>
+__device__ __forceinline__ void nl_pair(double xi, double yi, double zi, double xj, double yj, double zj, double L,
+                                        double invL, double rc2, double &fx, double &fy, double &fz, double &s12,
+                                        double &s6)
+{
+    double dx = xi - xj, dy = yi - yj, dz = zi - zj; // lj_potential_energy.f90:119-121
+    if (MIC) { dx = mic(dx, L, invL); dy = mic(dy, L, invL); dz = mic(dz, L, invL); } // :124-126
+    const double r2 = dist2(dx, dy, dz);             // :129
+    const bool in = r2 < rc2;                        // :132
+    double ir2 = nl_rcp(r2);
+    ir2 = in ? ir2 : 0.0;
+    const double ir6 = __dmul_rn(__dmul_rn(ir2, ir2), ir2);
+    const double ir12 = __dmul_rn(ir6, ir6);
+    s12 = __dadd_rn(s12, ir12);
+    s6 = __dadd_rn(s6, ir6);
+    const double g = __dmul_rn(fma(2.0, ir12, -ir6), ir2); // -dU_r / r^2 (:143,148)
+    fx = fma(g, dx, fx); fy = fma(g, dy, fy); fz = fma(g, dz, fz);
+}
+
+template <bool MIC>
+__device__ __forceinline__ void nl_walk(const int *__restrict__ nb, size_t stride, int cnt, const double *__restrict__ px,
+                                        const double *__restrict__ py, const double *__restrict__ pz, double xi,
+                                        double yi, double zi, double L, double invL, double rc2, double &fx,
+                                        double &fy, double &fz, double &s12, double &s6)
+{
+    int m = 0;
+    for (; m + 4 <= cnt; m += 4) {
+        int j[4];
+        double xj[4], yj[4], zj[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) j[u] = __ldg(nb + (size_t)(m + u) * stride);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { xj[u] = px[j[u]]; yj[u] = py[j[u]]; zj[u] = pz[j[u]]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) nl_pair<MIC>(xi, yi, zi, xj[u], yj[u], zj[u], L, invL, rc2, fx, fy, fz, s12, s6);
+    }
+    for (; m < cnt; ++m) {
+        const int j = __ldg(nb + (size_t)m * stride);
+        nl_pair<MIC>(xi, yi, zi, px[j], py[j], pz[j], L, invL, rc2, fx, fy, fz, s12, s6);
+    }
+}
+
+__device__ __forceinline__ double nl_drift_wrap(double x, double v, double acc, const SimConst &sc)
+{
+    const double xn = (x + v * sc.dt) + acc * sc.dt_square_half; // verlet.f90:58
+    return xn - sc.L * floor(xn * sc.invL);                      // geometry_pbc.f90:54-56
+}
+
+// Squared displacement of (x,y,z) from the build position of slot i (minimum image).
+__device__ __forceinline__ double nl_disp2(const NlArgs &a, int i, double x, double y, double z)
+{
+    const int n = a.sc.n;
+    const double dx = mic(x - a.r0[i], a.sc.L, a.sc.invL);
+    const double dy = mic(y - a.r0[(size_t)n + i], a.sc.L, a.sc.invL);
+    const double dz = mic(z - a.r0[2 * (size_t)n + i], a.sc.L, a.sc.invL);
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// CTA-wide maximum of a non-negative double, folded into ctl->maxd2_bits (bit patterns of
+// non-negative doubles order like unsigned integers => the atomic max is order-independent).
+__device__ __forceinline__ void nl_block_max(double d2, double *scratch, NlCtl *ctl)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d2 = fmax(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = d2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = scratch[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, scratch[w]);
+        if (m > 0.0) atomicMax(&ctl->maxd2_bits, (unsigned long long)__double_as_longlong(m));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// The step kernel.  MODE 0: forces + observables at rb[cur] (compute_lj_potential_energy).
+// MODE 1: one verlet_step: forces at rb[1-cur] (already drifted), both half kicks, E_kin,
+// unwrapped update, r(t+2dt) -> rb[cur], skin check; the last CTA flips cur.
+// ------------------------------------------------------------------------------------------
+template <int MODE, bool TRACK>
+__global__ void __launch_bounds__(NL_BS) nl_step_kernel(NlArgs a)
+{
+    __shared__ double scratch[5 * (NL_BS / 32)];
+    __shared__ bool is_last;
+    const int n = a.sc.n;
+    const int i = blockIdx.x * NL_BS + threadIdx.x;
+    const bool valid = i < n;
+    const int cur = a.ctl->cur;
+    const int ev = (MODE == 1) ? 1 - cur : cur;
+    const double *px = a.rb[ev], *py = px + n, *pz = py + n;
+    const double L = a.sc.L, invL = a.sc.invL, rc2 = a.sc.rc2;
+
+    double xi = 0.0, yi = 0.0, zi = 0.0;
+    int cnt = 0;
+    bool inter = true;
+    if (valid) {
+        xi = px[i]; yi = py[i]; zi = pz[i];
+        cnt = a.nb_cnt[i];
+        inter = a.interior[i] != 0;
+    }
+    const bool fast = __all_sync(0xffffffffu, inter) && (a.ctl->unwrapped == 0);
+    double fx = 0.0, fy = 0.0, fz = 0.0, s12 = 0.0, s6 = 0.0;
+    if (fast) nl_walk<false>(a.nbr + i, a.stride, cnt, px, py, pz, xi, yi, zi, L, invL, rc2, fx, fy, fz, s12, s6);
+    else nl_walk<true>(a.nbr + i, a.stride, cnt, px, py, pz, xi, yi, zi, L, invL, rc2, fx, fy, fz, s12, s6);
+
+    double s[5] = {s12, s6, 0.0, 0.0, 0.0};
+    double d2 = 0.0;
+    if (valid) {
+        const size_t ix = i, iy = ix + n, iz = iy + n;
+        const double axn = 24.0 * fx, ayn = 24.0 * fy, azn = 24.0 * fz; // lj_potential_energy.f90:189-191
+        double vx = a.v[ix], vy = a.v[iy], vz = a.v[iz];
+        if (MODE == 1) {
+            const double axo = a.a[ix], ayo = a.a[iy], azo = a.a[iz];
+            vx = vx + axo * a.sc.dt_half; vy = vy + ayo * a.sc.dt_half; vz = vz + azo * a.sc.dt_half; // verlet.f90:72-74
+            vx = vx + axn * a.sc.dt_half; vy = vy + ayn * a.sc.dt_half; vz = vz + azn * a.sc.dt_half; // verlet.f90:86-88
+            a.v[ix] = vx; a.v[iy] = vy; a.v[iz] = vz;
+            double *pr = a.rb[cur]; // r(t): read for the unwrapped update, then overwritten with r(t+2dt)
+            if (TRACK) { // md_simulation_program.f90:341-351 (dnint)
+                double dx = xi - pr[ix], dy = yi - pr[iy], dz = zi - pr[iz];
+                dx = dx - L * round(dx * invL);
+                dy = dy - L * round(dy * invL);
+                dz = dz - L * round(dz * invL);
+                a.ru[ix] = a.ru[ix] + dx; a.ru[iy] = a.ru[iy] + dy; a.ru[iz] = a.ru[iz] + dz;
+            }
+            const double xn = nl_drift_wrap(xi, vx, axn, a.sc); // verlet.f90:58-63 of the next step
+            const double yn = nl_drift_wrap(yi, vy, ayn, a.sc);
+            const double zn = nl_drift_wrap(zi, vz, azn, a.sc);
+            pr[ix] = xn; pr[iy] = yn; pr[iz] = zn;
+            d2 = nl_disp2(a, i, xn, yn, zn);
+        }
+        a.a[ix] = axn; a.a[iy] = ayn; a.a[iz] = azn;
+        s[2] = vx * vx; s[3] = vy * vy; s[4] = vz * vz; // verlet.f90:93-95
+    }
+    block_sum<5>(s, scratch);
+    if (MODE == 1) nl_block_max(d2, scratch, a.ctl);
+    if (threadIdx.x == 0) {
+        double *sp = a.spart + (size_t)blockIdx.x * 5;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) sp[q] = s[q];
+        __threadfence();
+        const unsigned t = atomicAdd(&a.ctl->ticket_step, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+
+    // fixed-order reduction of all CTA partials
+    double r[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int b = threadIdx.x; b < a.nblk; b += NL_BS) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) r[q] += __ldcg(a.spart + (size_t)b * 5 + q);
+    }
+    block_sum<5>(r, scratch);
+    if (threadIdx.x == 0) {
+        // ordered pairs: every unordered pair was counted twice
+        const double S12 = 0.5 * r[0], S6 = 0.5 * r[1];
+        double o[4];
+        o[0] = 4.0 * (S12 - S6) + a.sc.tail_u;                    // :140,188,221
+        o[1] = 0.5 * (r[2] + r[3] + r[4]);                        // verlet.f90:93-95
+        o[2] = 24.0 * fma(-2.0, S12, S6) + a.sc.tail_du;          // :143,192,222
+        o[3] = 24.0 * fma(26.0, S12, -7.0 * S6) + a.sc.tail_ddu;  // :178,193,223
+        a.obs[0] = o[0]; a.obs[1] = o[1]; a.obs[2] = o[2]; a.obs[3] = o[3];
+        if (MODE == 1) {
+            StepCtl *sc = a.sctl;
+            const long long step = sc->step;
+            if (sc->series && step < sc->series_cap) {
+                double *sr = sc->series + (size_t)step * 4;
+                sr[0] = o[0]; sr[1] = o[1]; sr[2] = o[2]; sr[3] = o[3];
+            }
+            sc->step = step + 1;
+            a.ctl->cur = 1 - cur;
+            a.ctl->unwrapped = 0; // every position the next step reads has been wrapped
+            const double m = __longlong_as_double((long long)a.ctl->maxd2_bits);
+            if (m > a.half_skin2) a.ctl->need_rebuild = 1;
+        }
+        a.ctl->ticket_step = 0;
+    }
+}
+
+// First step of a run: rb[1-cur] = wrap(drift(rb[cur], v, a)) (verlet.f90:58-63) + skin check.
+__global__ void __launch_bounds__(NL_BS) nl_drift_kernel(NlArgs a)
+{
+    __shared__ double scratch[NL_BS / 32];
+    const int n = a.sc.n;
+    const int i = blockIdx.x * NL_BS + threadIdx.x;
+    const int cur = a.ctl->cur;
+    double d2 = 0.0;
+    if (i < n) {
+        const double *ps = a.rb[cur];
+        double *pd = a.rb[1 - cur];
+        const size_t ix = i, iy = ix + n, iz = iy + n;
+        const double xn = nl_drift_wrap(ps[ix], a.v[ix], a.a[ix], a.sc);
+        const double yn = nl_drift_wrap(ps[iy], a.v[iy], a.a[iy], a.sc);
+        const double zn = nl_drift_wrap(ps[iz], a.v[iz], a.a[iz], a.sc);
+        pd[ix] = xn; pd[iy] = yn; pd[iz] = zn;
+        d2 = nl_disp2(a, i, xn, yn, zn);
+    }
+    nl_block_max(d2, scratch, a.ctl);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned t = atomicAdd(&a.ctl->ticket_drift, 1u);
+        if (t == gridDim.x - 1) {
+            a.ctl->ticket_drift = 0;
+            const double m = __longlong_as_double((long long)a.ctl->maxd2_bits);
+            if (m > a.half_skin2) a.ctl->need_rebuild = 1;
+        }
+    }
+}
+
+// Sets the condition of a CUDA-graph IF node from the device flag (graph path only).
+__global__ void nl_setcond_kernel(cudaGraphConditionalHandle h, const NlCtl *ctl)
+{
+    if (threadIdx.x == 0) cudaGraphSetConditional(h, ctl->need_rebuild ? 1u : 0u);
+}
+
+// ------------------------------------------------------------------------------------------
+// Order conversion (upload / download / tests)
+// ------------------------------------------------------------------------------------------
+// dst[q][orig[k]] = src_q[k]
+__global__ void __launch_bounds__(256) nl_to_orig_kernel(int n, int narr, NlArgs a, double *dst)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int o = a.orig[k];
+    for (int q = 0; q < narr; ++q) dst[(size_t)q * n + o] = a.arr[q][k];
+}
+
+__global__ void __launch_bounds__(256) nl_identity_kernel(int n, int *orig, int *slot_of_orig)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) { orig[k] = k; slot_of_orig[k] = k; }
+}
+
+// cell id of every atom in ORIGINAL numbering, from the sorted tables
+__global__ void __launch_bounds__(128) nl_cell_of_atom_kernel(int ncells, const int *start, const int *orig, int *out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    for (int k = start[c]; k < start[c + 1]; ++k) out[orig[k]] = c;
+}
+
+// in-cutoff / listed pair counts (ordered)
+__global__ void __launch_bounds__(NL_BS) nl_count_kernel(NlArgs a)
+{
+    const int n = a.sc.n;
+    const int i = blockIdx.x * NL_BS + threadIdx.x;
+    unsigned long long ncand = 0, ncut = 0;
+    if (i < n) {
+        const double *px = a.rb[a.ctl->cur], *py = px + n, *pz = py + n;
+        const double xi = px[i], yi = py[i], zi = pz[i];
+        const int cnt = a.nb_cnt[i];
+        for (int m = 0; m < cnt; ++m) {
+            const int j = a.nbr[(size_t)m * a.stride + i];
+            const double dx = mic(xi - px[j], a.sc.L, a.sc.invL);
+            const double dy = mic(yi - py[j], a.sc.L, a.sc.invL);
+            const double dz = mic(zi - pz[j], a.sc.L, a.sc.invL);
+            ++ncand;
+            if (dist2(dx, dy, dz) < a.sc.rc2) ++ncut;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        ncand += __shfl_xor_sync(0xffffffffu, ncand, o);
+        ncut += __shfl_xor_sync(0xffffffffu, ncut, o);
+    }
+    if ((threadIdx.x & 31) == 0 && a.pair_counts) { atomicAdd(&a.pair_counts[0], ncand); atomicAdd(&a.pair_counts[1], ncut); }
+}
+
+// ==========================================================================================
+// Host side
+// ==========================================================================================
+int nlist_cells_per_edge_host(const ljmd_params &p, double skin)
+{
+    // Largest nc with cell edge L/nc >= rc + skin (same back-off rule as the plain cell list).
+    const double range = p.rc + skin;
+    volatile double ratio = p.box_length / range;
+    int nc = (int)floor(ratio);
+    if (nc > 0 && (double)nc * range * (1.0 + 1e-12) > p.box_length) nc -= 1;
+    if (nc > 128) nc = 128;
+    return nc;
+}
+
+double nlist_default_skin()
+{
+    double skin = 0.3;
+    if (const char *e = getenv("LJMD_NL_SKIN")) skin = atof(e);
+    if (!(skin >= 0.0)) skin = 0.3;
+    return skin;
+}
+
+static NlArgs make_args(ljmd_ctx *c, int eval_sel)
+{
+    const NlistWork &w = c->nw;
+    NlArgs a;
+    a.sc = c->sc;
+    a.nc = w.nc; a.ncells = w.ncells; a.scale = w.scale;
+    a.rl2 = w.rl2; a.half_skin2 = w.half_skin2;
+    a.maxnb = w.maxnb; a.stride = w.stride;
+    a.rb[0] = c->rbuf[0]; a.rb[1] = c->rbuf[1];
+    a.v = c->st.vx; a.a = c->st.ax; a.ru = c->st.rux;
+    a.r0 = w.r0; a.alt = w.alt;
+    const size_t n = c->nR;
+    int q = 0;
+    for (int b = 0; b < 2; ++b) for (int k = 0; k < 3; ++k) a.arr[q++] = c->rbuf[b] + k * n;
+    for (int k = 0; k < 3; ++k) a.arr[q++] = c->st.vx + k * n;
+    for (int k = 0; k < 3; ++k) a.arr[q++] = c->st.ax + k * n;
+    if (c->st.rux) for (int k = 0; k < 3; ++k) a.arr[q++] = c->st.rux + k * n;
+    a.narr = q;
+    for (; q < 15; ++q) a.arr[q] = nullptr;
+    a.cell_of_slot = w.cell_of_slot; a.cell_count = w.cell_count; a.cell_start = w.cell_start;
+    a.cell_cursor = w.cell_cursor; a.keys = w.keys;
+    a.orig = w.orig; a.orig_alt = w.orig_alt; a.slot_of_orig = w.slot_of_orig;
+    a.interior = w.interior; a.nb_cnt = w.nb_cnt; a.nbr = w.nbr;
+    a.ctl = w.ctl; a.sctl = c->fw.ctl;
+    a.spart = w.spart; a.nblk = w.nblk;
+    a.obs = c->fw.obs;
+    a.eval_sel = eval_sel;
+    a.pair_counts = nullptr;
+    return a;
+}
+
+int nlist_plan(ljmd_ctx *c)
+{
+    NlistWork &w = c->nw;
+    if (c->R != 1) return set_error(LJMD_ERR_UNSUPPORTED, "neighbour list supports nreplicas == 1 only");
+    const int n = c->sc.n;
+    w.skin = nlist_default_skin();
+    w.nc = nlist_cells_per_edge_host(c->p, w.skin);
+    if (w.nc < 3)
+        return set_error(LJMD_ERR_UNSUPPORTED, "neighbour list needs floor(L/(rc+skin)) >= 3 (got %d)", w.nc);
+    w.ncells = w.nc * w.nc * w.nc;
+    w.scale = (double)w.nc * c->p.inv_box_length;
+    const double rl = c->p.rc + w.skin;
+    w.rl2 = rl * rl;
+    w.half_skin2 = 0.25 * w.skin * w.skin;
+    const double expect = 4.18879020478639 * rl * rl * rl * c->p.density;
+    int cap = (int)(1.6 * expect) + 24;
+    if (const char *e = getenv("LJMD_NL_CAP")) cap = atoi(e);
+    cap = std::max(8, std::min(cap, std::max(8, n - 1)));
+    w.maxnb = (cap + 3) / 4 * 4;
+    w.stride = ((size_t)n + 31) / 32 * 32;
+    w.nblk = (n + NL_BS - 1) / NL_BS;
+    w.narr = c->st.rux ? 15 : 12;
+    w.cur_host = 0;
+    LJMD_CUDA_CHECK(cudaMalloc(&w.cell_of_slot, sizeof(int) * (size_t)n));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.cell_count, sizeof(int) * (size_t)w.ncells));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.cell_start, sizeof(int) * ((size_t)w.ncells + 1)));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.cell_cursor, sizeof(int) * (size_t)w.ncells));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.keys, sizeof(unsigned long long) * (size_t)n));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.orig, sizeof(int) * (size_t)n));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.orig_alt, sizeof(int) * (size_t)n));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.slot_of_orig, sizeof(int) * (size_t)n));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.interior, (size_t)n));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.nb_cnt, sizeof(int) * (size_t)n));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.nbr, sizeof(int) * w.stride * (size_t)w.maxnb));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.r0, sizeof(double) * 3 * (size_t)n));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.alt, sizeof(double) * 15 * (size_t)n));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.spart, sizeof(double) * 5 * (size_t)w.nblk));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.ctl, sizeof(NlCtl)));
+    LJMD_CUDA_CHECK(cudaStreamCreateWithFlags(&w.side_stream, cudaStreamNonBlocking));
+    LJMD_CUDA_CHECK(cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (size_t)w.ncells, c->stream));
+    LJMD_CUDA_CHECK(cudaMemsetAsync(w.cell_cursor, 0, sizeof(int) * (size_t)w.ncells, c->stream));
+    LJMD_CUDA_CHECK(cudaMemsetAsync(w.nb_cnt, 0, sizeof(int) * (size_t)n, c->stream));
+    LJMD_CUDA_CHECK(cudaMemsetAsync(w.interior, 0, (size_t)n, c->stream));
+    LJMD_CUDA_CHECK(cudaMemsetAsync(w.r0, 0, sizeof(double) * 3 * (size_t)n, c->stream));
+    LJMD_CUDA_CHECK(cudaMemsetAsync(w.spart, 0, sizeof(double) * 5 * (size_t)w.nblk, c->stream));
+    LJMD_CUDA_CHECK(cudaMemsetAsync(w.ctl, 0, sizeof(NlCtl), c->stream));
+    nl_identity_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, w.orig, w.slot_of_orig);
+    LJMD_CUDA_CHECK(cudaGetLastError());
+    LJMD_TRY(nlist_request_rebuild(c));
+    return LJMD_OK;
+}
+
+void nlist_free(ljmd_ctx *c)
+{
+    NlistWork &w = c->nw;
+    cudaFree(w.cell_of_slot); cudaFree(w.cell_count); cudaFree(w.cell_start); cudaFree(w.cell_cursor);
+    cudaFree(w.keys); cudaFree(w.orig); cudaFree(w.orig_alt); cudaFree(w.slot_of_orig); cudaFree(w.interior);
+    cudaFree(w.nb_cnt); cudaFree(w.nbr); cudaFree(w.r0); cudaFree(w.alt); cudaFree(w.spart); cudaFree(w.ctl);
+    if (w.side_stream) cudaStreamDestroy(w.side_stream);
+}
+
+// Host-side write of selected NlCtl fields (stream-ordered).
+static int ctl_poke(ljmd_ctx *c, size_t offset, const void *src, size_t bytes)
+{
+    // the source must outlive the async copy: stage through the pinned obs scratch
+    char *stage = reinterpret_cast<char *>(c->h_obs) + sizeof(double) * 4 * (size_t)c->R;
+    memcpy(stage, src, bytes);
+    LJMD_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<char *>(c->nw.ctl) + offset, stage, bytes, cudaMemcpyHostToDevice,
+                                    c->stream));
+    LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return LJMD_OK;
+}
+
+int nlist_request_rebuild(ljmd_ctx *c)
+{
+    const int one = 1;
+    return ctl_poke(c, offsetof(NlCtl, need_rebuild), &one, sizeof(int));
+}
+
+// The rebuild sequence (every kernel is a no-op unless the device flag is set).
+int nlist_enqueue_rebuild(ljmd_ctx *c, int eval_sel)
+{
+    const NlistWork &w = c->nw;
+    const int n = c->sc.n;
+    const NlArgs a = make_args(c, eval_sel);
+    nl_bin_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(a);
+    nl_scan_kernel<<<1, 1024, 0, c->stream>>>(a);
+    nl_fill_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(a);
+    nl_sortcell_kernel<<<(w.ncells + 127) / 128, 128, 0, c->stream>>>(a);
+    nl_permute_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(a);
+    nl_copyback_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(a);
+    nl_build_kernel<<<w.nblk, NL_BS, 0, c->stream>>>(a);
+    if (!c->capturing) c->launches += 7;
+    LJMD_CUDA_CHECK(cudaGetLastError());
+    return LJMD_OK;
+}
+
+int nlist_enqueue_forces(ljmd_ctx *c)
+{
+    LJMD_TRY(nlist_enqueue_rebuild(c, 0));
+    const NlArgs a = make_args(c, 0);
+    nl_step_kernel<0, false><<<c->nw.nblk, NL_BS, 0, c->stream>>>(a);
+    if (!c->capturing) c->launches++;
+    LJMD_CUDA_CHECK(cudaGetLastError());
+    return LJMD_OK;
+}
+
+int nlist_enqueue_drift(ljmd_ctx *c)
+{
+    const NlArgs a = make_args(c, 0);
+    nl_drift_kernel<<<c->nw.nblk, NL_BS, 0, c->stream>>>(a);
+    if (!c->capturing) c->launches++;
+    LJMD_CUDA_CHECK(cudaGetLastError());
+    return LJMD_OK;
+}
+
+int nlist_enqueue_step_kernel(ljmd_ctx *c)
+{
+    const NlArgs a = make_args(c, 1);
+    if (c->st.rux) nl_step_kernel<1, true><<<c->nw.nblk, NL_BS, 0, c->stream>>>(a);
+    else nl_step_kernel<1, false><<<c->nw.nblk, NL_BS, 0, c->stream>>>(a);
+    if (!c->capturing) c->launches++;
+    LJMD_CUDA_CHECK(cudaGetLastError());
+    c->nw.cur_host ^= 1;
+    return LJMD_OK;
+}
+
+// One velocity-Verlet step (rb[1-cur] must already hold the drifted positions).
+int nlist_enqueue_step(ljmd_ctx *c)
+{
+    LJMD_TRY(nlist_enqueue_rebuild(c, 1));
+    return nlist_enqueue_step_kernel(c);
+}
+
+// `nsteps` steps as a CUDA graph in which the rebuild sequence of every step sits inside an IF
+// node whose condition is the device flag: a step that needs no rebuild costs two launches
+// (the 1-thread condition kernel and the step kernel).
+int nlist_capture_graph(ljmd_ctx *c, int nsteps, cudaGraphExec_t *out)
+{
+    cudaGraph_t g = nullptr;
+    LJMD_CUDA_CHECK(cudaGraphCreate(&g, 0));
+    cudaStream_t s = c->stream;
+    cudaError_t e = cudaStreamBeginCaptureToGraph(s, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); LJMD_CUDA_CHECK(e); }
+    c->capturing = true;
+    int rc = LJMD_OK;
+    const int cur_save = c->nw.cur_host;
+    std::vector<cudaGraph_t> bodies;
+    for (int st = 0; st < nsteps && rc == LJMD_OK; ++st) {
+        cudaGraphConditionalHandle h;
+        e = cudaGraphConditionalHandleCreate(&h, g, 0, cudaGraphCondAssignDefault);
+        if (e != cudaSuccess) { rc = set_error(LJMD_ERR_CUDA, "cudaGraphConditionalHandleCreate: %s", cudaGetErrorString(e)); break; }
+        nl_setcond_kernel<<<1, 32, 0, s>>>(h, c->nw.ctl);
+        cudaStreamCaptureStatus status;
+        const cudaGraphNode_t *deps = nullptr;
+        size_t ndeps = 0;
+        e = cudaStreamGetCaptureInfo(s, &status, nullptr, nullptr, &deps, &ndeps);
+        if (e != cudaSuccess) { rc = set_error(LJMD_ERR_CUDA, "cudaStreamGetCaptureInfo: %s", cudaGetErrorString(e)); break; }
+        cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+        cp.conditional.handle = h;
+        cp.conditional.type = cudaGraphCondTypeIf;
+        cp.conditional.size = 1;
+        cudaGraphNode_t cnode;
+        e = cudaGraphAddNode(&cnode, g, deps, ndeps, &cp);
+        if (e != cudaSuccess) { rc = set_error(LJMD_ERR_CUDA, "cudaGraphAddNode(conditional): %s", cudaGetErrorString(e)); break; }
+        bodies.push_back(cp.conditional.phGraph_out[0]);
+        e = cudaStreamUpdateCaptureDependencies(s, &cnode, 1, cudaStreamSetCaptureDependencies);
+        if (e != cudaSuccess) { rc = set_error(LJMD_ERR_CUDA, "cudaStreamUpdateCaptureDependencies: %s", cudaGetErrorString(e)); break; }
+        rc = nlist_enqueue_step_kernel(c);
+    }
+    cudaGraph_t g2 = nullptr;
+    e = cudaStreamEndCapture(s, &g2);
+    if (rc == LJMD_OK && e != cudaSuccess) rc = set_error(LJMD_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    // bodies of the IF nodes: the rebuild sequence, captured on a side stream
+    for (size_t b = 0; b < bodies.size() && rc == LJMD_OK; ++b) {
+        e = cudaStreamBeginCaptureToGraph(c->nw.side_stream, bodies[b], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) { rc = set_error(LJMD_ERR_CUDA, "capture of the rebuild body: %s", cudaGetErrorString(e)); break; }
+        c->stream = c->nw.side_stream;
+        rc = nlist_enqueue_rebuild(c, 1);
+        c->stream = s;
+        cudaGraph_t dummy = nullptr;
+        e = cudaStreamEndCapture(c->nw.side_stream, &dummy);
+        if (rc == LJMD_OK && e != cudaSuccess) rc = set_error(LJMD_ERR_CUDA, "end capture of the rebuild body: %s", cudaGetErrorString(e));
+    }
+    c->capturing = false;
+    c->nw.cur_host = cur_save; // capture does not execute anything
+    if (rc != LJMD_OK) { cudaGraphDestroy(g); return rc; }
+    e = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    LJMD_CUDA_CHECK(e);
+    return LJMD_OK;
+}
+
+// State in ORIGINAL order into w.alt: arrays [r(3) | v(3) | a(3) | ru(3)] (positions = rb[cur]).
+int nlist_gather_orig(ljmd_ctx *c)
+{
+    const NlistWork &w = c->nw;
+    const int n = c->sc.n;
+    NlArgs a = make_args(c, 0);
+    const size_t nn = c->nR;
+    int q = 0;
+    for (int k = 0; k < 3; ++k) a.arr[q++] = c->rbuf[w.cur_host] + k * nn;
+    for (int k = 0; k < 3; ++k) a.arr[q++] = c->st.vx + k * nn;
+    for (int k = 0; k < 3; ++k) a.arr[q++] = c->st.ax + k * nn;
+    if (c->st.rux) for (int k = 0; k < 3; ++k) a.arr[q++] = c->st.rux + k * nn;
+    nl_to_orig_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, q, a, w.alt);
+    c->launches++;
+    LJMD_CUDA_CHECK(cudaGetLastError());
+    return LJMD_OK;
+}
+
+// Puts the resident state back into ORIGINAL order with cur = 0 (before an upload).
+int nlist_canonicalize(ljmd_ctx *c)
+{
+    NlistWork &w = c->nw;
+    const int n = c->sc.n;
+    const size_t nn = c->nR, bytes = sizeof(double) * nn;
+    LJMD_TRY(nlist_gather_orig(c));
+    LJMD_CUDA_CHECK(cudaMemcpyAsync(c->rbuf[0], w.alt, 3 * bytes, cudaMemcpyDeviceToDevice, c->stream));
+    LJMD_CUDA_CHECK(cudaMemcpyAsync(c->st.vx, w.alt + 3 * nn, 3 * bytes, cudaMemcpyDeviceToDevice, c->stream));
+    LJMD_CUDA_CHECK(cudaMemcpyAsync(c->st.ax, w.alt + 6 * nn, 3 * bytes, cudaMemcpyDeviceToDevice, c->stream));
+    if (c->st.rux) LJMD_CUDA_CHECK(cudaMemcpyAsync(c->st.rux, w.alt + 9 * nn, 3 * bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return nlist_reset_identity(c); // keeps the rebuild counter
+}
+
+// The state arrays were just overwritten in ORIGINAL order (drop-in calls): identity permutation,
+// cur = 0, list invalid.
+int nlist_reset_identity(ljmd_ctx *c)
+{
+    NlistWork &w = c->nw;
+    const int n = c->sc.n;
+    nl_identity_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, w.orig, w.slot_of_orig);
+    LJMD_CUDA_CHECK(cudaGetLastError());
+    c->launches++;
+    NlCtl h;
+    memset(&h, 0, sizeof(h));
+    h.need_rebuild = 1;
+    LJMD_TRY(ctl_poke(c, 0, &h, offsetof(NlCtl, rebuilds)));
+    w.cur_host = 0;
+    return LJMD_OK;
+}
+
+int nlist_check_overflow(ljmd_ctx *c)
+{
+    NlCtl h;
+    LJMD_CUDA_CHECK(cudaMemcpyAsync(&h, c->nw.ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->nw.rebuilds_host = h.rebuilds;
+    if (h.overflow > 0)
+        return set_error(LJMD_ERR_UNSUPPORTED,
+                         "neighbour list capacity exceeded: an atom has %d neighbours within rc+skin, capacity %d "
+                         "(set LJMD_NL_CAP)", h.overflow, c->nw.maxnb);
+    return LJMD_OK;
+}
+
+int nlist_pair_counts(ljmd_ctx *c, unsigned long long *d_counts)
+{
+    LJMD_TRY(nlist_enqueue_rebuild(c, 0));
+    NlArgs a = make_args(c, 0);
+    a.pair_counts = d_counts;
+    nl_count_kernel<<<c->nw.nblk, NL_BS, 0, c->stream>>>(a);
+    c->launches++;
+    LJMD_CUDA_CHECK(cudaGetLastError());
+    return LJMD_OK;
+}
+
+int nlist_download_cells(ljmd_ctx *c, int32_t *cell_of_atom, int32_t *cell_start, int32_t *order)
+{
+    const NlistWork &w = c->nw;
+    const int n = c->sc.n;
+    cudaError_t e = cudaSuccess;
+    if (cell_of_atom) {
+        // cell_of_slot is scratch between rebuilds: reuse it for the original-numbering table
+        nl_cell_of_atom_kernel<<<(w.ncells + 127) / 128, 128, 0, c->stream>>>(w.ncells, w.cell_start, w.orig, w.cell_of_slot);
+        e = cudaMemcpyAsync(cell_of_atom, w.cell_of_slot, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (e == cudaSuccess && cell_start)
+        e = cudaMemcpyAsync(cell_start, w.cell_start, sizeof(int) * ((size_t)w.ncells + 1), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && order)
+        e = cudaMemcpyAsync(order, w.orig, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return set_error(LJMD_ERR_CUDA, "ljmd_ctx_download_cells(): %s", cudaGetErrorString(e));
+    return LJMD_OK;
+}
+
+} // namespace ljmd
+
+using namespace ljmd;
+
+extern "C" int ljmd_ctx_nlist_info(ljmd_ctx *c, double *skin, int32_t *cells_per_edge, int32_t *capacity,
+                                   int64_t *rebuilds, int64_t *entries)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_nlist_info(): ctx is NULL.");
+    if (c->method != LJMD_METHOD_NLIST)
+        return set_error(LJMD_ERR_ARG, "ljmd_ctx_nlist_info(): context does not use the neighbour list.");
+    int prev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
+    int rc = nlist_check_overflow(c);
+    long long total = 0;
+    if (rc == LJMD_OK && entries) {
+        std::vector<int> cnt(c->sc.n);
+        cudaError_t e = cudaMemcpy(cnt.data(), c->nw.nb_cnt, sizeof(int) * (size_t)c->sc.n, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = set_error(LJMD_ERR_CUDA, "ljmd_ctx_nlist_info(): %s", cudaGetErrorString(e));
+        for (int v : cnt) total += v;
+    }
+    if (prev != c->device) cudaSetDevice(prev);
+    if (rc != LJMD_OK) return rc;
+    if (skin) *skin = c->nw.skin;
+    if (cells_per_edge) *cells_per_edge = c->nw.nc;
+    if (capacity) *capacity = c->nw.maxnb;
+    if (rebuilds) *rebuilds = c->nw.rebuilds_host;
+    if (entries) *entries = total;
+    return LJMD_OK;
+}
+
+// Neighbour list of the last build in ORIGINAL atom numbering: counts[n]; the neighbours of atom i,
+// ascending, at nbr[i*cap .. i*cap + counts[i]).
+extern "C" int ljmd_ctx_download_nlist(ljmd_ctx *c, int32_t *counts, int32_t *nbr, int32_t cap)
+{
+    clear_error();
+    if (!c || !counts || !nbr) return set_error(LJMD_ERR_NULL, "ljmd_ctx_download_nlist(): NULL argument.");
+    if (c->method != LJMD_METHOD_NLIST)
+        return set_error(LJMD_ERR_ARG, "ljmd_ctx_download_nlist(): context does not use the neighbour list.");
+    const NlistWork &w = c->nw;
+    const int n = c->sc.n;
+    int prev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
+    std::vector<int> h_orig(n), h_cnt(n), h_nbr(w.stride * (size_t)w.maxnb);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(h_orig.data(), w.orig, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(h_cnt.data(), w.nb_cnt, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(h_nbr.data(), w.nbr, sizeof(int) * h_nbr.size(), cudaMemcpyDeviceToHost);
+    if (prev != c->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return set_error(LJMD_ERR_CUDA, "ljmd_ctx_download_nlist(): %s", cudaGetErrorString(e));
+    for (int k = 0; k < n; ++k) {
+        const int o = h_orig[k], m = h_cnt[k];
+        if (m > cap) return set_error(LJMD_ERR_ARG, "ljmd_ctx_download_nlist(): cap %d < %d neighbours.", cap, m);
+        counts[o] = m;
+        int32_t *dst = nbr + (size_t)o * cap;
+        for (int q = 0; q < m; ++q) dst[q] = h_orig[h_nbr[(size_t)q * w.stride + k]];
+        std::sort(dst, dst + m);
+    }
+    return LJMD_OK;
+}

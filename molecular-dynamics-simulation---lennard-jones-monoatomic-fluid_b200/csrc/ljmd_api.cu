@@ -6,6 +6,7 @@
 // There is no CPU fallback in this library: every compute entry point needs a CUDA device.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <mutex>
@@ -149,9 +150,43 @@ static int set_ctl(ljmd_ctx *c, long long cap, double *series)
 
 // nsteps velocity-Verlet steps.  Invariant outside this function: rbuf[0] (the state block's
 // rx..rz) holds the current positions.
+static int run_steps_nlist(ljmd_ctx *c, int nsteps)
+{
+    LJMD_TRY(nlist_enqueue_drift(c)); // r(t+dt) of the first step -> rb[1-cur]
+    int done = 0;
+    if (c->timing) {
+        for (; done < nsteps; ++done) {
+            LJMD_TRY(nlist_enqueue_rebuild(c, 1));
+            LJMD_CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
+            LJMD_TRY(nlist_enqueue_step_kernel(c));
+            LJMD_CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
+            LJMD_CUDA_CHECK(cudaEventSynchronize(c->ev1));
+            float ms = 0.f;
+            LJMD_CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+            c->force_ms += ms;
+            c->force_evals += 1;
+        }
+        return LJMD_OK;
+    }
+    const int G = 32; // even: a chunk leaves NlCtl::cur unchanged
+    if (nsteps >= G && !getenv("LJMD_NL_NOGRAPH")) {
+        if (!c->graph_chunk) {
+            LJMD_TRY(nlist_capture_graph(c, G, &c->graph_chunk));
+            c->graph_chunk_steps = G;
+        }
+        for (; done + G <= nsteps; done += G) {
+            LJMD_CUDA_CHECK(cudaGraphLaunch(c->graph_chunk, c->stream));
+            c->launches += (int64_t)G * 2; // condition kernel + step kernel; rebuilds are added at the next sync
+        }
+    }
+    for (; done < nsteps; ++done) LJMD_TRY(nlist_enqueue_step(c));
+    return LJMD_OK;
+}
+
 static int run_steps(ljmd_ctx *c, int nsteps)
 {
     if (nsteps <= 0) return LJMD_OK;
+    if (c->method == LJMD_METHOD_NLIST) return run_steps_nlist(c, nsteps);
     LJMD_TRY(launch_drift(c, 0, 1)); // r(t+dt) of the first step
     int done = 0;
     if (c->timing) {
@@ -195,6 +230,12 @@ static int fetch_obs(ljmd_ctx *c, double *dst, int per_rep, const int *idx)
     if (dst)
         for (int r = 0; r < c->R; ++r)
             for (int k = 0; k < per_rep; ++k) dst[(size_t)r * per_rep + k] = c->h_obs[4 * r + idx[k]];
+    if (c->method == LJMD_METHOD_NLIST) {
+        LJMD_TRY(nlist_check_overflow(c));
+        // list builds that ran inside graph IF nodes: 7 kernels each
+        if (c->graph_chunk) c->launches += 7 * (c->nw.rebuilds_host - c->nw.rebuilds_counted);
+        c->nw.rebuilds_counted = c->nw.rebuilds_host;
+    }
     return LJMD_OK;
 }
 
@@ -265,6 +306,7 @@ extern "C" int ljmd_ctx_destroy(ljmd_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     drop_graphs(c);
     cellwork_free(c);
+    nlist_free(c);
     cudaFree(c->state_block);
     cudaFree(c->pw.fpart);
     cudaFree(c->pw.spart);
@@ -299,7 +341,7 @@ extern "C" int ljmd_ctx_create(const ljmd_params *params, const ljmd_options *op
     ljmd_options o = {LJMD_METHOD_AUTO, -1, 1, 0};
     if (opts) o = *opts;
     if (o.nreplicas < 1) return set_error(LJMD_ERR_ARG, "ljmd_ctx_create(): nreplicas must be >= 1.");
-    if (o.method < LJMD_METHOD_AUTO || o.method > LJMD_METHOD_CELLS)
+    if (o.method < LJMD_METHOD_AUTO || o.method > LJMD_METHOD_NLIST)
         return set_error(LJMD_ERR_ARG, "ljmd_ctx_create(): unknown method %d.", o.method);
 
     int ndev = 0;
@@ -321,13 +363,19 @@ extern "C" int ljmd_ctx_create(const ljmd_params *params, const ljmd_options *op
     c->nR = (size_t)params->n * c->R;
 
     const int nc = cells_per_edge_host(*params);
+    const int nc_nl = nlist_cells_per_edge_host(*params, nlist_default_skin());
     int method = o.method;
     if (method == LJMD_METHOD_AUTO)
-        method = (nc >= 4 && params->n >= 16384) ? LJMD_METHOD_CELLS : LJMD_METHOD_ALLPAIRS;
+        method = (nc_nl >= 4 && params->n >= 8192 && o.nreplicas == 1) ? LJMD_METHOD_NLIST : LJMD_METHOD_ALLPAIRS;
     if (method == LJMD_METHOD_CELLS && nc < 3) {
         delete c;
         return set_error(LJMD_ERR_UNSUPPORTED,
                          "ljmd_ctx_create(): cell list needs floor(L/rc) >= 3 (got %d).", nc);
+    }
+    if (method == LJMD_METHOD_NLIST && nc_nl < 3) {
+        delete c;
+        return set_error(LJMD_ERR_UNSUPPORTED,
+                         "ljmd_ctx_create(): neighbour list needs floor(L/(rc+skin)) >= 3 (got %d).", nc_nl);
     }
     c->method = method;
 
@@ -386,6 +434,7 @@ extern "C" int ljmd_ctx_create(const ljmd_params *params, const ljmd_options *op
     CREATE_CHECK(cudaMallocHost(&c->h_obs, sizeof(double) * 4 * (size_t)c->R + 64));
 
     if (method == LJMD_METHOD_CELLS) CREATE_TRY(cellwork_plan(c));
+    else if (method == LJMD_METHOD_NLIST) CREATE_TRY(nlist_plan(c));
     else CREATE_TRY(pairwork_plan(c));
     CREATE_CHECK(cudaStreamSynchronize(c->stream));
 #undef CREATE_CHECK
@@ -403,6 +452,8 @@ extern "C" int ljmd_ctx_upload(ljmd_ctx *c, const double *rx, const double *ry, 
     DeviceGuard g;
     LJMD_TRY(g.enter(c->device));
     LJMD_TRY(ensure_stage(c));
+    // the neighbour-list path keeps the state cell-sorted: back to original order first
+    if (c->method == LJMD_METHOD_NLIST) LJMD_TRY(nlist_canonicalize(c));
     const double *src[9] = {rx, ry, rz, vx, vy, vz, ax, ay, az};
     const size_t bytes = sizeof(double) * c->nR;
     // pack contiguous runs of non-NULL arrays into the pinned stage, one H2D per run
@@ -434,13 +485,18 @@ extern "C" int ljmd_ctx_download(ljmd_ctx *c, double *rx, double *ry, double *rz
     LJMD_TRY(ensure_stage(c));
     double *dst[9] = {rx, ry, rz, vx, vy, vz, ax, ay, az};
     const size_t bytes = sizeof(double) * c->nR;
+    const double *dev_src = c->state_block;
+    if (c->method == LJMD_METHOD_NLIST) { // un-sort into the scratch block first
+        LJMD_TRY(nlist_gather_orig(c));
+        dev_src = c->nw.alt;
+    }
     int k = 0;
     while (k < 9) {
         if (!dst[k]) { ++k; continue; }
         int e = k;
         while (e < 9 && dst[e]) ++e;
         LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_stage + (size_t)k * c->nR,
-                                        c->state_block + (size_t)k * c->nR, bytes * (e - k),
+                                        dev_src + (size_t)k * c->nR, bytes * (e - k),
                                         cudaMemcpyDeviceToHost, c->stream));
         k = e;
     }
@@ -461,6 +517,10 @@ extern "C" int ljmd_ctx_download_unwrapped(ljmd_ctx *c, double *rux, double *ruy
     const size_t bytes = sizeof(double) * c->nR;
     double *dst[3] = {rux, ruy, ruz};
     double *srcs[3] = {c->st.rux, c->st.ruy, c->st.ruz};
+    if (c->method == LJMD_METHOD_NLIST) {
+        LJMD_TRY(nlist_gather_orig(c));
+        for (int k = 0; k < 3; ++k) srcs[k] = c->nw.alt + (size_t)(9 + k) * c->nR;
+    }
     for (int k = 0; k < 3; ++k)
         if (dst[k]) LJMD_CUDA_CHECK(cudaMemcpyAsync(dst[k], srcs[k], bytes, cudaMemcpyDeviceToHost, c->stream));
     LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -473,8 +533,12 @@ extern "C" int ljmd_ctx_compute_forces(ljmd_ctx *c, double *obs3)
     if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_compute_forces(): ctx is NULL.");
     DeviceGuard g;
     LJMD_TRY(g.enter(c->device));
-    LJMD_TRY(enqueue_force(c, 0));
-    LJMD_TRY(launch_finalize(c, 0, 0, 0, 0));
+    if (c->method == LJMD_METHOD_NLIST) {
+        LJMD_TRY(nlist_enqueue_forces(c));
+    } else {
+        LJMD_TRY(enqueue_force(c, 0));
+        LJMD_TRY(launch_finalize(c, 0, 0, 0, 0));
+    }
     const int idx[3] = {0, 2, 3};
     return fetch_obs(c, obs3, 3, idx);
 }
@@ -577,6 +641,8 @@ extern "C" int ljmd_ctx_device_ptrs(ljmd_ctx *c, double **pos0, double **pos1, d
 {
     clear_error();
     if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_device_ptrs(): ctx is NULL.");
+    if (c->method == LJMD_METHOD_NLIST)
+        return set_error(LJMD_ERR_UNSUPPORTED, "ljmd_ctx_device_ptrs(): the neighbour-list path keeps its state in cell-sorted order; use ljmd_ctx_download.");
     if (pos0) *pos0 = c->rbuf[0];
     if (pos1) *pos1 = c->rbuf[1];
     if (vel) *vel = c->st.vx;
@@ -660,7 +726,7 @@ extern "C" int ljmd_tail_corrections(const ljmd_params *p, double *tail_epot, do
 }
 
 extern "C" int ljmd_ctx_method(const ljmd_ctx *c) { return c ? c->method : -1; }
-extern "C" int ljmd_ctx_cells_per_edge(const ljmd_ctx *c) { return c ? c->cw.nc : 0; }
+extern "C" int ljmd_ctx_cells_per_edge(const ljmd_ctx *c) { return c ? (c->method == LJMD_METHOD_NLIST ? c->nw.nc : c->cw.nc) : 0; }
 extern "C" int64_t ljmd_ctx_launch_count(const ljmd_ctx *c) { return c ? c->launches : 0; }
 
 extern "C" int ljmd_ctx_force_timing(ljmd_ctx *c, int32_t enable, double *ms_total, int64_t *n_evals)
@@ -683,7 +749,8 @@ extern "C" int ljmd_ctx_pair_counts(ljmd_ctx *c, int64_t *n_candidates, int64_t 
     LJMD_TRY(g.enter(c->device));
     if (!c->fw.pair_counts) LJMD_CUDA_CHECK(cudaMalloc(&c->fw.pair_counts, 2 * sizeof(unsigned long long) * c->R));
     LJMD_CUDA_CHECK(cudaMemsetAsync(c->fw.pair_counts, 0, 2 * sizeof(unsigned long long) * c->R, c->stream));
-    int rc = enqueue_force(c, 0); // positions unchanged: recomputes the same partials, plus counts
+    int rc = (c->method == LJMD_METHOD_NLIST) ? nlist_pair_counts(c, c->fw.pair_counts)
+                                              : enqueue_force(c, 0); // positions unchanged: recomputes the same partials, plus counts
     unsigned long long h[2] = {0, 0};
     if (rc == LJMD_OK) {
         cudaError_t e = cudaMemcpyAsync(h, c->fw.pair_counts, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
@@ -737,6 +804,11 @@ int compat_ctx(const ljmd_params *p, const char *who, ljmd_ctx **out)
     if (g_compat && g_compat->method == LJMD_METHOD_CELLS && cells_per_edge_host(*p) != g_compat->cw.nc) {
         ljmd_ctx_destroy(g_compat); g_compat = nullptr;
     }
+    if (g_compat && g_compat->method == LJMD_METHOD_NLIST &&
+        (nlist_cells_per_edge_host(*p, g_compat->nw.skin) != g_compat->nw.nc || p->rc != g_compat->p.rc ||
+         p->density != g_compat->p.density)) {
+        ljmd_ctx_destroy(g_compat); g_compat = nullptr;
+    }
     if (!g_compat) {
         ljmd_options o = {LJMD_METHOD_AUTO, -1, 1, 0};
         LJMD_TRY(ljmd_ctx_create(p, &o, &g_compat));
@@ -778,17 +850,28 @@ extern "C" int ljmd_compute_lj(const ljmd_params *params, const double *rx, cons
     memcpy(c->h_stage + c->nR, ry, nb);
     memcpy(c->h_stage + 2 * c->nR, rz, nb);
     LJMD_CUDA_CHECK(cudaMemcpyAsync(c->st.rx, c->h_stage, 3 * nb, cudaMemcpyHostToDevice, c->stream));
-    LJMD_TRY(enqueue_force(c, 0));
-    LJMD_TRY(launch_finalize(c, 0, 0, 0, 0));
-    // accelerations and obs are contiguous: ax ay az | obs
-    LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_stage + 6 * c->nR, c->st.ax, 3 * nb + sizeof(double) * 4,
-                                    cudaMemcpyDeviceToHost, c->stream));
+    if (c->method == LJMD_METHOD_NLIST) {
+        LJMD_TRY(nlist_reset_identity(c));
+        LJMD_TRY(nlist_enqueue_forces(c));
+        LJMD_TRY(nlist_gather_orig(c)); // accelerations back in original order
+        LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_stage + 6 * c->nR, c->nw.alt + 6 * c->nR, 3 * nb,
+                                        cudaMemcpyDeviceToHost, c->stream));
+        LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_stage + 9 * c->nR, c->fw.obs, sizeof(double) * 4,
+                                        cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        LJMD_TRY(enqueue_force(c, 0));
+        LJMD_TRY(launch_finalize(c, 0, 0, 0, 0));
+        // accelerations and obs are contiguous: ax ay az | obs
+        LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_stage + 6 * c->nR, c->st.ax, 3 * nb + sizeof(double) * 4,
+                                        cudaMemcpyDeviceToHost, c->stream));
+    }
     LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     memcpy(ax, c->h_stage + 6 * c->nR, nb);
     memcpy(ay, c->h_stage + 7 * c->nR, nb);
     memcpy(az, c->h_stage + 8 * c->nR, nb);
     const double *o = c->h_stage + 9 * c->nR;
     *epot = o[0]; *d_epot = o[2]; *dd_epot = o[3];
+    if (c->method == LJMD_METHOD_NLIST) LJMD_TRY(nlist_check_overflow(c));
     return LJMD_OK;
 }
 
@@ -813,11 +896,22 @@ extern "C" int ljmd_verlet_step(const ljmd_params *params, double *rx, double *r
     double *arr[9] = {rx, ry, rz, vx, vy, vz, ax, ay, az};
     for (int k = 0; k < 9; ++k) memcpy(c->h_stage + (size_t)k * c->nR, arr[k], nb);
     LJMD_CUDA_CHECK(cudaMemcpyAsync(c->state_block, c->h_stage, 9 * nb, cudaMemcpyHostToDevice, c->stream));
-    LJMD_TRY(launch_drift(c, 0, 1));
-    LJMD_TRY(enqueue_step(c, 0, 2)); // mode 2: the new positions are copied back into rbuf[0]
-    LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_stage, c->state_block, 9 * nb + sizeof(double) * 4,
-                                    cudaMemcpyDeviceToHost, c->stream));
+    if (c->method == LJMD_METHOD_NLIST) {
+        LJMD_TRY(nlist_reset_identity(c));
+        LJMD_TRY(nlist_enqueue_drift(c));
+        LJMD_TRY(nlist_enqueue_step(c));
+        LJMD_TRY(nlist_gather_orig(c)); // r(t+dt), v, a back in original order
+        LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_stage, c->nw.alt, 9 * nb, cudaMemcpyDeviceToHost, c->stream));
+        LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_stage + 9 * c->nR, c->fw.obs, sizeof(double) * 4,
+                                        cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        LJMD_TRY(launch_drift(c, 0, 1));
+        LJMD_TRY(enqueue_step(c, 0, 2)); // mode 2: the new positions are copied back into rbuf[0]
+        LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_stage, c->state_block, 9 * nb + sizeof(double) * 4,
+                                        cudaMemcpyDeviceToHost, c->stream));
+    }
     LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (c->method == LJMD_METHOD_NLIST) LJMD_TRY(nlist_check_overflow(c));
     for (int k = 0; k < 9; ++k) memcpy(arr[k], c->h_stage + (size_t)k * c->nR, nb);
     const double *o = c->h_stage + 9 * c->nR;
     *epot = o[0]; *ekin = o[1]; *d_epot = o[2]; *dd_epot = o[3];

@@ -121,6 +121,39 @@ struct CellWork {
     double pair_weight; // 0.5 if the force kernel visits ordered pairs, 1.0 if unordered
 };
 
+// Device control block of the neighbour-list path (lj_nlist.cu).  The fields up to `rebuilds`
+// are reset together when the host puts the state back into original order.
+struct NlCtl {
+    int need_rebuild;      // set by the drift / step epilogue (max displacement > skin/2) or the host
+    int cur;               // index of the position buffer that holds r(t); flips every step
+    int overflow;          // largest neighbour count seen if it exceeded the capacity, else 0
+    int unwrapped;         // the last build saw positions outside [0, L]: minimum image everywhere
+    unsigned ticket_step, ticket_build, ticket_drift; // last-CTA tickets
+    unsigned pad_;
+    unsigned long long maxd2_bits; // max squared displacement since the last build (double bits)
+    long long rebuilds;    // number of list builds so far
+};
+
+// Neighbour-list work buffers (lj_nlist.cu).  The resident state is kept in cell-sorted order.
+struct NlistWork {
+    int nc, ncells;      // cells per edge (edge >= rc + skin), nc^3
+    double scale;        // nc / L
+    double skin, rl2, half_skin2;
+    int maxnb;           // list capacity per atom
+    size_t stride;       // entry m of slot i is nbr[m*stride + i]
+    int nblk, narr;
+    int cur_host;        // host mirror of NlCtl::cur
+    long long rebuilds_host, rebuilds_counted;
+    int *cell_of_slot, *cell_count, *cell_start, *cell_cursor;
+    unsigned long long *keys;
+    int *orig, *orig_alt, *slot_of_orig;
+    unsigned char *interior;
+    int *nb_cnt, *nbr;
+    double *r0, *alt, *spart;
+    NlCtl *ctl;
+    cudaStream_t side_stream; // captures the IF-node bodies of the step graph
+};
+
 } // namespace ljmd
 
 // The opaque context of the public ABI.
@@ -146,6 +179,7 @@ struct ljmd_ctx {
     ljmd::PairWork pw;
     ljmd::FinalizeWork fw;
     ljmd::CellWork cw;
+    ljmd::NlistWork nw;
     double *h_obs; // pinned [R][4] (+ scratch)
     double *h_stage; // pinned staging for host<->device state copies (9*nR doubles)
     // graphs
@@ -186,5 +220,24 @@ int cellwork_plan(ljmd_ctx *c);
 void cellwork_free(ljmd_ctx *c);
 int launch_cells_force(ljmd_ctx *c, int buf);
 int cells_per_edge_host(const ljmd_params &p);
+
+// ---- lj_nlist.cu -------------------------------------------------------------------------
+int nlist_plan(ljmd_ctx *c);
+void nlist_free(ljmd_ctx *c);
+int nlist_cells_per_edge_host(const ljmd_params &p, double skin);
+double nlist_default_skin();
+int nlist_request_rebuild(ljmd_ctx *c);
+int nlist_enqueue_rebuild(ljmd_ctx *c, int eval_sel);
+int nlist_enqueue_forces(ljmd_ctx *c);      // rebuild-if-needed + forces/observables at r(t)
+int nlist_enqueue_drift(ljmd_ctx *c);       // first step of a run
+int nlist_enqueue_step(ljmd_ctx *c);        // rebuild-if-needed + fused step kernel
+int nlist_enqueue_step_kernel(ljmd_ctx *c); // the fused step kernel alone
+int nlist_capture_graph(ljmd_ctx *c, int nsteps, cudaGraphExec_t *out);
+int nlist_gather_orig(ljmd_ctx *c);         // state in original order -> nw.alt [r v a (ru)]
+int nlist_canonicalize(ljmd_ctx *c);
+int nlist_reset_identity(ljmd_ctx *c);
+int nlist_check_overflow(ljmd_ctx *c);
+int nlist_pair_counts(ljmd_ctx *c, unsigned long long *d_counts);
+int nlist_download_cells(ljmd_ctx *c, int32_t *cell_of_atom, int32_t *cell_start, int32_t *order);
 
 } // namespace ljmd

@@ -432,44 +432,55 @@ int orc_run_steps(const orc_params *p, int32_t nsteps, double *rx, double *ry, d
 /* ==========================================================================================
  * Cell-list oracle (no reference counterpart; definition in ljmd_oracle.h).
  * ======================================================================================== */
-int32_t orc_cells_per_edge(const orc_params *p)
+int32_t orc_cells_per_edge_range(const orc_params *p, double range)
 {
-    /* Largest ncell with cell edge L/ncell >= rc, backed off by one if the edge is within
-     * 1e-12 relative of rc so that a rounding in floor(x*scale) can never separate an in-cutoff
+    /* Largest ncell with cell edge L/ncell >= range, backed off by one if the edge is within
+     * 1e-12 relative of range so that a rounding in floor(x*scale) can never separate an in-range
      * pair by two cells. */
-    int32_t nc = (int32_t)floor(p->box_length / p->rc);
-    if (nc > 0 && (double)nc * p->rc * (1.0 + 1e-12) > p->box_length) nc -= 1;
+    int32_t nc = (int32_t)floor(p->box_length / range);
+    if (nc > 0 && (double)nc * range * (1.0 + 1e-12) > p->box_length) nc -= 1;
     if (nc > 128) nc = 128; /* bounded cell table: at most 128^3 cells */
     return nc;
 }
 
-static inline int32_t orc_cell_coord(double x, double scale, int32_t nc)
+int32_t orc_cells_per_edge(const orc_params *p) { return orc_cells_per_edge_range(p, p->rc); }
+
+static inline int32_t orc_cell_coord(double x, double L, double invL, double scale, int32_t nc)
 {
+    /* out-of-box coordinates (unwrapped input, geometry_pbc.f90:18-19) are wrapped for binning */
+    if (x < 0.0 || x > L) x = x - L * floor(x * invL);
     int32_t c = (int32_t)floor(x * scale);
     if (c < 0) c = 0;
     if (c > nc - 1) c = nc - 1; /* wrapped x may equal L exactly */
     return c;
 }
 
-int orc_cell_assign(const orc_params *p, const double *rx, const double *ry, const double *rz,
-                    int32_t *cell_of_atom)
+int orc_cell_assign_range(const orc_params *p, double range, const double *rx, const double *ry,
+                          const double *rz, int32_t *cell_of_atom)
 {
-    const int32_t nc = orc_cells_per_edge(p);
+    const int32_t nc = orc_cells_per_edge_range(p, range);
     if (nc < 3) return ORC_ERR_RC;
     const double scale = (double)nc * p->inv_box_length;
+    const double L = p->box_length, invL = p->inv_box_length;
     for (int32_t i = 0; i < p->n; ++i) {
-        const int32_t cx = orc_cell_coord(rx[i], scale, nc);
-        const int32_t cy = orc_cell_coord(ry[i], scale, nc);
-        const int32_t cz = orc_cell_coord(rz[i], scale, nc);
+        const int32_t cx = orc_cell_coord(rx[i], L, invL, scale, nc);
+        const int32_t cy = orc_cell_coord(ry[i], L, invL, scale, nc);
+        const int32_t cz = orc_cell_coord(rz[i], L, invL, scale, nc);
         cell_of_atom[i] = (cx * nc + cy) * nc + cz;
     }
     return ORC_OK;
 }
 
-int orc_cell_sort(const orc_params *p, const int32_t *cell_of_atom, int32_t *cell_start,
-                  int32_t *order)
+int orc_cell_assign(const orc_params *p, const double *rx, const double *ry, const double *rz,
+                    int32_t *cell_of_atom)
 {
-    const int32_t nc = orc_cells_per_edge(p);
+    return orc_cell_assign_range(p, p->rc, rx, ry, rz, cell_of_atom);
+}
+
+int orc_cell_sort_range(const orc_params *p, double range, const int32_t *cell_of_atom,
+                        int32_t *cell_start, int32_t *order)
+{
+    const int32_t nc = orc_cells_per_edge_range(p, range);
     if (nc < 3) return ORC_ERR_RC;
     const int32_t ncells = nc * nc * nc;
     memset(cell_start, 0, sizeof(int32_t) * ((size_t)ncells + 1));
@@ -481,6 +492,68 @@ int orc_cell_sort(const orc_params *p, const int32_t *cell_of_atom, int32_t *cel
     for (int32_t i = 0; i < p->n; ++i) order[fill[cell_of_atom[i]]++] = i; /* stable */
     free(fill);
     return ORC_OK;
+}
+
+int orc_cell_sort(const orc_params *p, const int32_t *cell_of_atom, int32_t *cell_start,
+                  int32_t *order)
+{
+    return orc_cell_sort_range(p, p->rc, cell_of_atom, cell_start, order);
+}
+
+static int orc_cmp_i32(const void *a, const void *b)
+{
+    const int32_t x = *(const int32_t *)a, y = *(const int32_t *)b;
+    return (x > y) - (x < y);
+}
+
+/* Verlet neighbour list (no reference counterpart): j is a neighbour of i iff the minimum-image
+ * r_ij^2, computed exactly as lj_potential_energy.f90:119-129 computes it, is < range^2.
+ * Full list (both i->j and j->i), each atom's neighbours ascending.  counts[n], nbr[n*cap]. */
+int orc_neighbor_list(const orc_params *p, double range, const double *rx, const double *ry,
+                      const double *rz, int32_t cap, int32_t *counts, int32_t *nbr)
+{
+    const int32_t n = p->n;
+    const int32_t nc = orc_cells_per_edge_range(p, range);
+    if (nc < 3) return ORC_ERR_RC;
+    const int32_t ncells = nc * nc * nc;
+    int32_t *cell = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+    int32_t *start = (int32_t *)malloc(sizeof(int32_t) * ((size_t)ncells + 1));
+    int32_t *order = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+    if (!cell || !start || !order) { free(cell); free(start); free(order); return ORC_ERR_NULL; }
+    orc_cell_assign_range(p, range, rx, ry, rz, cell);
+    orc_cell_sort_range(p, range, cell, start, order);
+    const double L = p->box_length, invL = p->inv_box_length, range2 = range * range;
+    int rc_ = ORC_OK;
+    for (int32_t i = 0; i < n && rc_ == ORC_OK; ++i) {
+        const int32_t ci = cell[i];
+        const int32_t cx = ci / (nc * nc), cy = (ci / nc) % nc, cz = ci % nc;
+        int32_t cnt = 0;
+        /* visit every distinct neighbour cell once (nc == 3: the 27 offsets cover the box once) */
+        for (int32_t ox = -1; ox <= 1; ++ox)
+            for (int32_t oy = -1; oy <= 1; ++oy)
+                for (int32_t oz = -1; oz <= 1; ++oz) {
+                    const int32_t nx = (cx + ox + nc) % nc, ny = (cy + oy + nc) % nc,
+                                  nz = (cz + oz + nc) % nc;
+                    const int32_t cj = (nx * nc + ny) * nc + nz;
+                    for (int32_t k = start[cj]; k < start[cj + 1]; ++k) {
+                        const int32_t j = order[k];
+                        if (j == i) continue;
+                        double dx = rx[i] - rx[j], dy = ry[i] - ry[j], dz = rz[i] - rz[j];
+                        dx = orc_minimum_image(dx, L, invL);
+                        dy = orc_minimum_image(dy, L, invL);
+                        dz = orc_minimum_image(dz, L, invL);
+                        const double rij2 = dx * dx + dy * dy + dz * dz;
+                        if (rij2 < range2) {
+                            if (cnt >= cap) { rc_ = ORC_ERR_N; break; }
+                            nbr[(size_t)i * cap + cnt++] = j;
+                        }
+                    }
+                }
+        counts[i] = cnt;
+        qsort(nbr + (size_t)i * cap, (size_t)cnt, sizeof(int32_t), orc_cmp_i32);
+    }
+    free(cell); free(start); free(order);
+    return rc_;
 }
 
 int orc_compute_lj_cells(const orc_params *p, const double *rx, const double *ry,

@@ -143,6 +143,18 @@ int orc_cell_assign(const orc_params *p, const double *rx, const double *ry, con
 /* cell_start has ncell^3+1 entries; order[k] = original index of the k-th atom in sorted order. */
 int orc_cell_sort(const orc_params *p, const int32_t *cell_of_atom, int32_t *cell_start,
                   int32_t *order);
+/* The same definitions for an arbitrary interaction range (the neighbour-list path bins with
+ * range = rc + skin); orc_cells_per_edge(p) == orc_cells_per_edge_range(p, p->rc). */
+int32_t orc_cells_per_edge_range(const orc_params *p, double range);
+int orc_cell_assign_range(const orc_params *p, double range, const double *rx, const double *ry,
+                          const double *rz, int32_t *cell_of_atom);
+int orc_cell_sort_range(const orc_params *p, double range, const int32_t *cell_of_atom,
+                        int32_t *cell_start, int32_t *order);
+/* Verlet neighbour list: j is listed for i iff the minimum-image r_ij^2 (operation order of
+ * lj_potential_energy.f90:119-129) is < range^2.  counts[n]; neighbours of i ascending at
+ * nbr[i*cap ...].  Returns ORC_ERR_N if an atom has more than cap neighbours. */
+int orc_neighbor_list(const orc_params *p, double range, const double *rx, const double *ry,
+                      const double *rz, int32_t cap, int32_t *counts, int32_t *nbr);
 int orc_compute_lj_cells(const orc_params *p, const double *rx, const double *ry,
                          const double *rz, double *ax, double *ay, double *az, double *epot,
                          double *d_epot, double *dd_epot, int64_t *n_candidates,

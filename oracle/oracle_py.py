@@ -59,6 +59,7 @@ def lib(variant: str = "O2") -> C.CDLL:
         L.orc_random_uniform.restype = C.c_double
         L.orc_count_pairs_in_cutoff.restype = C.c_int64
         L.orc_cells_per_edge.restype = C.c_int32
+        L.orc_cells_per_edge_range.restype = C.c_int32
         _LIBS[variant] = L
     return _LIBS[variant]
 
@@ -205,3 +206,30 @@ def cell_sort(p: OrcParams, cell: np.ndarray):
     order = np.zeros(p.n, dtype=np.int32)
     _chk(lib().orc_cell_sort(C.byref(p), _ip(cell), _ip(start), _ip(order)))
     return start, order
+
+
+def cells_per_edge_range(p: OrcParams, rng: float) -> int:
+    return lib().orc_cells_per_edge_range(C.byref(p), C.c_double(rng))
+
+
+def cell_assign_range(p: OrcParams, rng: float, rx, ry, rz) -> np.ndarray:
+    cell = np.zeros(p.n, dtype=np.int32)
+    _chk(lib().orc_cell_assign_range(C.byref(p), C.c_double(rng), _p(rx), _p(ry), _p(rz), _ip(cell)))
+    return cell
+
+
+def cell_sort_range(p: OrcParams, rng: float, cell: np.ndarray):
+    nc = cells_per_edge_range(p, rng)
+    start = np.zeros(nc ** 3 + 1, dtype=np.int32)
+    order = np.zeros(p.n, dtype=np.int32)
+    _chk(lib().orc_cell_sort_range(C.byref(p), C.c_double(rng), _ip(cell), _ip(start), _ip(order)))
+    return start, order
+
+
+def neighbor_list(p: OrcParams, rng: float, rx, ry, rz, cap: int):
+    """Full Verlet list within `rng` (original numbering, ascending): (counts[n], nbr[n, cap])."""
+    counts = np.zeros(p.n, dtype=np.int32)
+    nbr = np.full((p.n, cap), -1, dtype=np.int32)
+    _chk(lib().orc_neighbor_list(C.byref(p), C.c_double(rng), _p(rx), _p(ry), _p(rz), cap,
+                                 _ip(counts), _ip(nbr)))
+    return counts, nbr

@@ -1,0 +1,247 @@
+"""GPU parity tests of the neighbour-list path (LJMD_METHOD_NLIST): counting-sort cells + Verlet
+list with skin + one fused kernel per step, state kept in cell-sorted order on the device.
+
+No reference counterpart (the reference is all-pairs only, lj_potential_energy.f90:109-183):
+forces / U / virial are checked against the all-pairs (or cell) oracle to 1e-12 relative per
+step, the integer cell assignment and the neighbour sets bit-exactly against the oracle's
+definitions (orc_cell_assign_range / orc_cell_sort_range / orc_neighbor_list)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import make_config, melt, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _state(lj, arrs):
+    return lj.SimState.from_arrays([a.copy() for a in arrs])
+
+
+class _env:
+    def __init__(self, **kv):
+        self.kv = kv
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        for k, v in self.kv.items():
+            os.environ[k] = str(v)
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _small(O):
+    g = np.load(os.path.join(GOLD, "cells_n864.npz"))
+    p_o = O.params_init(864, float(g["L"]), 1e-3, 2.5, 6)
+    s = [np.ascontiguousarray(a).copy() for a in g["state300"]]
+    return p_o, s
+
+
+def _check_integers(lj, O, ctx, p_o, s):
+    info = ctx.nlist_info()
+    rng = p_o.rc + info["skin"]
+    assert info["cells_per_edge"] == O.cells_per_edge_range(p_o, rng)
+    cell, start, order = ctx.download_cells()
+    cell_o = O.cell_assign_range(p_o, rng, *s[:3])
+    start_o, order_o = O.cell_sort_range(p_o, rng, cell_o)
+    assert np.array_equal(cell, cell_o) and np.array_equal(start, start_o) and np.array_equal(order, order_o)
+    counts, nbr = ctx.download_nlist()
+    counts_o, nbr_o = O.neighbor_list(p_o, rng, *s[:3], cap=info["capacity"])
+    assert np.array_equal(counts, counts_o)
+    assert np.array_equal(nbr, nbr_o)
+    assert info["entries"] == int(counts_o.sum())
+    return info
+
+
+def test_nlist_forces_and_integers_n864(lj, O):
+    p_o, s = _small(O)
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    ax, ay, az, e, d_, dd = O.compute_lj(p_o, *s[:3])
+    with lj.Context(p, method=lj.METHOD_NLIST) as ctx:
+        assert ctx.method == lj.METHOD_NLIST
+        ctx.upload(_state(lj, s))
+        obs = ctx.compute_forces()
+        got = ctx.download()
+        info = _check_integers(lj, O, ctx, p_o, s)
+        cand, cut = ctx.pair_counts()
+    assert info["rebuilds"] == 1
+    assert cut == O.count_pairs_in_cutoff(p_o, *s[:3]) and 2 * cand == info["entries"]
+    assert rel_err(got.ax, ax) <= TOL and rel_err(got.ay, ay) <= TOL and rel_err(got.az, az) <= TOL
+    for g_, w_ in zip(obs, (e, d_, dd)):
+        assert abs(g_ - w_) <= TOL * abs(w_)
+    # the state comes back in ORIGINAL order, untouched
+    for k, name in enumerate(("rx", "ry", "rz", "vx", "vy", "vz")):
+        assert np.array_equal(getattr(got, name), s[k]), name
+
+
+def test_nlist_vs_oracle_32k(lj, O):
+    p_o, st = make_config(O, "cfg3")
+    s = melt(O, p_o, st, 20, cells=True)
+    ax, ay, az, e, d_, dd, _, ncut = O.compute_lj_cells(p_o, *s[:3])
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    with lj.Context(p) as ctx:  # AUTO -> neighbour list at N=32000
+        assert ctx.method == lj.METHOD_NLIST and ctx.cells_per_edge == 12
+        ctx.upload(_state(lj, s))
+        obs = ctx.compute_forces()
+        got = ctx.download(("ax", "ay", "az"))
+        _check_integers(lj, O, ctx, p_o, s)
+        _, cut = ctx.pair_counts()
+    assert cut == ncut
+    assert rel_err(got.ax, ax) <= TOL and rel_err(got.ay, ay) <= TOL and rel_err(got.az, az) <= TOL
+    for g_, w_ in zip(obs, (e, d_, dd)):
+        assert abs(g_ - w_) <= TOL * abs(w_)
+
+
+def test_nlist_single_step_parity_32k(lj, O):
+    """One verlet_step through the drop-in C-ABI call (AUTO -> neighbour list) from a melted state."""
+    p_o, st = make_config(O, "cfg3")
+    s0 = melt(O, p_o, st, 10, cells=True)
+    ref = [a.copy() for a in s0]
+    ref_obs = O.verlet_step(p_o, ref, cells=True)
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    s = _state(lj, s0)
+    obs = lj.verlet_step(p, s)
+    for got, want in zip(obs, ref_obs):
+        assert abs(got - want) <= TOL * abs(want)
+    for name, want in zip(lj.SimState.NAMES, ref):
+        assert rel_err(getattr(s, name), want) <= TOL, name
+    assert np.array_equal(s.rx, ref[0]) and np.array_equal(s.ry, ref[1]) and np.array_equal(s.rz, ref[2])
+    lj.compat_release()
+
+
+def test_nlist_multistep_rebuilds_graph_and_determinism(lj, O):
+    """70 steps with a small skin (several list rebuilds): CUDA-graph path (IF-node rebuilds) ==
+    eager path bitwise, run-to-run bitwise, and within 1e-9 of the oracle trajectory."""
+    p_o, st = make_config(O, "cfg3")
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    nsteps = 70
+    ref = [a.copy() for a in st]
+    for _ in range(nsteps):
+        ref_obs = O.verlet_step(p_o, ref, cells=True)
+
+    def run(**env):
+        with _env(LJMD_NL_SKIN=0.12, **env):
+            with lj.Context(p, method=lj.METHOD_NLIST) as ctx:
+                ctx.upload(_state(lj, st))
+                ctx.compute_forces()
+                obs = ctx.step(nsteps)
+                d = ctx.download()
+                info = ctx.nlist_info()
+        return obs.copy(), [a.copy() for a in d.arrays()], info
+
+    a = run()
+    b = run()
+    c = run(LJMD_NL_NOGRAPH=1)
+    assert a[2]["rebuilds"] >= 3, a[2]
+    assert a[2]["rebuilds"] == c[2]["rebuilds"]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[0], c[0])
+    for x, y, z in zip(a[1], b[1], c[1]):
+        assert np.array_equal(x, y) and np.array_equal(x, z)
+    assert np.all(np.abs(a[0] - np.array(ref_obs)) <= 1e-9 * np.abs(np.array(ref_obs)))
+    assert rel_err(a[1][0], ref[0]) <= 1e-9 and rel_err(a[1][3], ref[3]) <= 1e-9
+
+
+def test_nlist_skin_independence(lj, O):
+    """The forces do not depend on the skin (the list always contains every in-cutoff pair)."""
+    p_o, s = _small(O)
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    outs = []
+    for skin in (0.0, 0.3, 0.6):
+        with _env(LJMD_NL_SKIN=skin):
+            with lj.Context(p, method=lj.METHOD_NLIST) as ctx:
+                ctx.upload(_state(lj, s))
+                ctx.compute_forces()
+                obs = ctx.step(12)
+                outs.append((obs.copy(), ctx.download().ax.copy(), ctx.nlist_info()["rebuilds"]))
+    assert outs[0][2] > outs[2][2]  # skin 0 rebuilds every step
+    for o in outs[1:]:
+        assert np.all(np.abs(o[0] - outs[0][0]) <= 1e-11 * np.abs(outs[0][0]))
+        assert rel_err(o[1], outs[0][1]) <= 1e-10
+
+
+def test_nlist_unwrapped_tracking(lj, O):
+    p_o, s = _small(O)
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    nsteps = 25
+    a0 = O.compute_lj(p_o, *s[:3])
+    ref = [x.copy() for x in s[:6]] + [a0[0].copy(), a0[1].copy(), a0[2].copy()]
+    ru = [x.copy() for x in s[:3]]
+    O.run_steps(p_o, nsteps, ref, ru=ru)
+    with _env(LJMD_NL_SKIN=0.1):
+        with lj.Context(p, method=lj.METHOD_NLIST, flags=lj.FLAG_TRACK_UNWRAPPED) as ctx:
+            ctx.upload(_state(lj, s))
+            ctx.compute_forces()
+            ctx.step(nsteps)
+            got_ru = ctx.download_unwrapped()
+            got = ctx.download()
+            assert ctx.nlist_info()["rebuilds"] >= 2
+    for k in range(3):
+        assert rel_err(got_ru[k], ru[k]) <= 1e-11
+    assert rel_err(got.rx, ref[0]) <= 1e-11
+
+
+def test_nlist_unwrapped_inputs(lj, O):
+    """The force routine is specified for unwrapped inputs too (geometry_pbc.f90:18-19)."""
+    p_o, s = _small(O)
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    ax, ay, az, e, d_, dd = O.compute_lj(p_o, *s[:3])
+    rng = np.random.default_rng(11)
+    su = [a.copy() for a in s]
+    for k in range(3):
+        su[k] = su[k] + p_o.box_length * rng.integers(-2, 3, size=p_o.n)
+    with lj.Context(p, method=lj.METHOD_NLIST) as ctx:
+        ctx.upload(_state(lj, su))
+        obs = ctx.compute_forces()
+        got = ctx.download(("ax", "ay", "az"))
+        obs5 = ctx.step(5)
+    assert rel_err(got.ax, ax) <= 1e-11 and rel_err(got.az, az) <= 1e-11
+    assert abs(obs[0] - e) <= 1e-11 * abs(e)
+    ref = [a.copy() for a in su[:6]] + [ax.copy(), ay.copy(), az.copy()]
+    ref_obs = O.run_steps(p_o, 5, ref)
+    assert np.all(np.abs(obs5 - np.array(ref_obs)) <= 1e-10 * np.abs(np.array(ref_obs)))
+
+
+def test_nlist_partial_upload_and_restart(lj, O):
+    """Uploading only velocities into a sorted resident state keeps positions / order intact."""
+    p_o, s = _small(O)
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    with lj.Context(p, method=lj.METHOD_NLIST) as ctx:
+        ctx.upload(_state(lj, s))
+        ctx.compute_forces()
+        ctx.step(7)
+        mid = ctx.download()
+        newv = [0.5 * mid.vx, 0.5 * mid.vy, 0.5 * mid.vz]
+        ctx.upload(vx=newv[0], vy=newv[1], vz=newv[2])
+        after = ctx.download()
+        assert np.array_equal(after.rx, mid.rx) and np.array_equal(after.ax, mid.ax)
+        assert np.array_equal(after.vx, newv[0])
+        obs = ctx.step(3)
+    ref = [mid.rx.copy(), mid.ry.copy(), mid.rz.copy()] + [v.copy() for v in newv] + [mid.ax.copy(), mid.ay.copy(), mid.az.copy()]
+    ref_obs = O.run_steps(p_o, 3, ref)
+    assert np.all(np.abs(obs - np.array(ref_obs)) <= 1e-11 * np.abs(np.array(ref_obs)))
+
+
+def test_nlist_capacity_overflow_is_an_error(lj, O):
+    p_o, s = _small(O)
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    with _env(LJMD_NL_CAP=16):
+        with lj.Context(p, method=lj.METHOD_NLIST) as ctx:
+            ctx.upload(_state(lj, s))
+            with pytest.raises(lj.LjmdError) as ei:
+                ctx.compute_forces()
+            assert ei.value.code == 10 and "capacity" in ei.value.message
+
+
+def test_nlist_needs_three_cells(lj):
+    p = lj.init_params(500, 10.0, 1e-4, 4.9, 5)
+    with pytest.raises(lj.LjmdError) as ei:
+        lj.Context(p, method=lj.METHOD_NLIST)
+    assert ei.value.code == 10

@@ -267,7 +267,7 @@ def test_cells_vs_oracle_32k(lj, O):
     s = melt(O, p_o, st, 20, cells=True)
     ax, ay, az, e, d_, dd, ncand, ncut = O.compute_lj_cells(p_o, *s[:3])
     p = lj.SimParams.from_buffer_copy(bytes(p_o))
-    with lj.Context(p) as ctx:   # AUTO -> cells at N=32000, 13 cells per edge
+    with lj.Context(p, method=lj.METHOD_CELLS) as ctx:   # 13 cells per edge at N=32000
         assert ctx.method == lj.METHOD_CELLS and ctx.cells_per_edge == 13
         ctx.upload(_state(lj, s))
         obs = ctx.compute_forces()

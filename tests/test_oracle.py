@@ -166,3 +166,40 @@ def test_unwrap_matches_displacement(O):
     for w, u in zip(s[:3], ru):
         k = (u - w) / p.box_length
         assert np.abs(k - np.round(k)).max() < 1e-9
+
+
+def test_neighbor_list_oracle_matches_bruteforce(O):
+    """orc_neighbor_list (cells, range rc+skin) == brute-force numpy minimum-image search."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cells_n864.npz"))
+    L = float(g["L"])
+    p = O.params_init(864, L, 1e-3, 2.5, 6)
+    s = [np.ascontiguousarray(a) for a in g["state300"]]
+    rng = 2.8
+    assert O.cells_per_edge_range(p, rng) == 3 and O.cells_per_edge_range(p, 2.5) == O.cells_per_edge(p) == 4
+    counts, nbr = O.neighbor_list(p, rng, *s[:3], cap=160)
+    pos = np.stack(s[:3], -1)
+    d = pos[:, None, :] - pos[None, :, :]
+    d = d - L * np.sign(d * (1.0 / L)) * np.floor(np.abs(d * (1.0 / L)) + 0.5)  # dnint
+    r2 = d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1] + d[..., 2] * d[..., 2]
+    np.fill_diagonal(r2, np.inf)
+    want = r2 < rng * rng
+    assert np.array_equal(counts, want.sum(1).astype(np.int32))
+    for i in (0, 17, 400, 863):
+        assert np.array_equal(nbr[i, :counts[i]], np.nonzero(want[i])[0].astype(np.int32))
+    # symmetric: j in list(i) <=> i in list(j)
+    pairs = {(i, int(j)) for i in range(864) for j in nbr[i, :counts[i]]}
+    assert all((j, i) in pairs for (i, j) in pairs)
+    # range cells: same definition as the rc cells with another edge
+    cell = O.cell_assign_range(p, rng, *s[:3])
+    start, order = O.cell_sort_range(p, rng, cell)
+    assert start[-1] == 864 and np.array_equal(np.sort(order), np.arange(864))
+    assert np.all(np.diff(cell[order]) >= 0)
+
+
+def test_cell_binning_wraps_out_of_box_input(O):
+    p = O.params_init(864, 12.0, 1e-3, 2.5, 6)
+    x = np.array([0.5, 12.5, -11.5, 24.5] + [1.0] * 860)
+    y = np.full(864, 1.0)
+    cell = O.cell_assign(p, x, y, y.copy())
+    assert cell[0] == cell[1] == cell[2] == cell[3]
