@@ -51,6 +51,7 @@ struct NlArgs {
     int maxnb;
     size_t stride;
     double *rb[2];     // position buffers: x array; y, z follow at +n, +2n
+    double4 *p4[2];    // the same positions packed (x, y, z, 0): one 32-byte sector per atom for the gathers
     double *v, *a;     // x arrays; y, z at +n, +2n
     double *ru;        // unwrapped x array or nullptr
     double *r0;        // [3][n] positions at the last list build
@@ -70,6 +71,25 @@ struct NlArgs {
     int eval_sel;  // rebuild kernels: 0 = the list is for rb[cur], 1 = for rb[1-cur]
     unsigned long long *pair_counts;
 };
+
+// Entry m of slot i: the list is stored in groups of four entries (one 16-byte load per thread),
+// group g of all slots contiguous (a warp reads 512 contiguous bytes per group).
+__host__ __device__ __forceinline__ size_t nl_entry(size_t stride, int i, int m)
+{
+    return (((size_t)(m >> 2) * stride + (size_t)i) << 2) + (size_t)(m & 3);
+}
+
+// 256-bit read-only load (LDG.E.256 on sm_100a): one packed position.
+__device__ __forceinline__ double4 nl_ld_pos(const double4 *p)
+{
+    double4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void nl_st_pos(double4 *p, double x, double y, double z)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x), "d"(y), "d"(z), "d"(0.0) : "memory");
+}
 
 // 1/x to <= 1 ulp (see lj_allpairs.cu).
 __device__ __forceinline__ double nl_rcp(double x)
@@ -220,7 +240,6 @@ __global__ void __launch_bounds__(NL_BS) nl_build_kernel(NlArgs a)
         const int zlo = cz - 1, zhi = cz + 1;
         const bool whole = (nc <= 3);
         int cnt = 0;
-        int *nb = a.nbr + i;
         for (int ox = -1; ox <= 1; ++ox) {
             const int nx = (cx + ox + nc) % nc;
             for (int oy = -1; oy <= 1; ++oy) {
@@ -245,15 +264,18 @@ __global__ void __launch_bounds__(NL_BS) nl_build_kernel(NlArgs a)
                         const double dz = mic(zi - pz[j], L, invL);
                         const double r2 = dist2(dx, dy, dz);
                         if (r2 < rl2 && j != i) {
-                            if (cnt < a.maxnb) nb[(size_t)cnt * a.stride] = j;
+                            if (cnt < a.maxnb) a.nbr[nl_entry(a.stride, i, cnt)] = j;
                             ++cnt;
                         }
                     }
                 }
             }
         }
-        a.nb_cnt[i] = min(cnt, a.maxnb);
         if (cnt > a.maxnb) atomicMax(&a.ctl->overflow, cnt);
+        cnt = min(cnt, a.maxnb);
+        a.nb_cnt[i] = cnt;
+        for (int m = cnt; m & 3; ++m) a.nbr[nl_entry(a.stride, i, m)] = i; // pad the last group (masked in the walk)
+        nl_st_pos(a.p4[a.ctl->cur ^ a.eval_sel] + i, xi, yi, zi);
         a.r0[i] = xi; a.r0[(size_t)n + i] = yi; a.r0[2 * (size_t)n + i] = zi;
         const bool inter = cx >= 1 && cx <= nc - 2 && cy >= 1 && cy <= nc - 2 && cz >= 1 && cz <= nc - 2;
         a.interior[i] = inter ? 1 : 0;
@@ -275,15 +297,16 @@ __global__ void __launch_bounds__(NL_BS) nl_build_kernel(NlArgs a)
 // ------------------------------------------------------------------------------------------
 // Per-pair body, branch-free: an entry outside the cutoff contributes exact zeros.
 // ------------------------------------------------------------------------------------------
-template <bool MIC>
-__device__ __forceinline__ void nl_pair(double xi, double yi, double zi, double xj, double yj, double zj, double L,
+template <bool MIC, bool MASKED>
+__device__ __forceinline__ void nl_pair(double xi, double yi, double zi, const double4 pj, bool keep, double L,
                                         double invL, double rc2, double &fx, double &fy, double &fz, double &s12,
                                         double &s6)
 {
-    double dx = xi - xj, dy = yi - yj, dz = zi - zj; // lj_potential_energy.f90:119-121
+    double dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z; // lj_potential_energy.f90:119-121
     if (MIC) { dx = mic(dx, L, invL); dy = mic(dy, L, invL); dz = mic(dz, L, invL); } // :124-126
     const double r2 = dist2(dx, dy, dz);             // :129
-    const bool in = r2 < rc2;                        // :132
+    bool in = r2 < rc2;                              // :132
+    if (MASKED) in = in && keep;                     // padding entries of the last group
     double ir2 = nl_rcp(r2);
     ir2 = in ? ir2 : 0.0;
     const double ir6 = __dmul_rn(__dmul_rn(ir2, ir2), ir2);
@@ -294,26 +317,36 @@ __device__ __forceinline__ void nl_pair(double xi, double yi, double zi, double 
     fx = fma(g, dx, fx); fy = fma(g, dy, fy); fz = fma(g, dz, fz);
 }
 
+// Walk of one atom's list.  The index groups stream from HBM (read once: cache-streaming loads,
+// prefetched two groups ahead); the packed positions are gathered from L1/L2.
 template <bool MIC>
-__device__ __forceinline__ void nl_walk(const int *__restrict__ nb, size_t stride, int cnt, const double *__restrict__ px,
-                                        const double *__restrict__ py, const double *__restrict__ pz, double xi,
-                                        double yi, double zi, double L, double invL, double rc2, double &fx,
-                                        double &fy, double &fz, double &s12, double &s6)
+__device__ __forceinline__ void nl_walk(const int4 *__restrict__ nb, size_t stride, int cnt,
+                                        const double4 *__restrict__ pos, double xi, double yi, double zi, double L,
+                                        double invL, double rc2, double &fx, double &fy, double &fz, double &s12,
+                                        double &s6)
 {
-    int m = 0;
-    for (; m + 4 <= cnt; m += 4) {
-        int j[4];
-        double xj[4], yj[4], zj[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) j[u] = __ldg(nb + (size_t)(m + u) * stride);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { xj[u] = px[j[u]]; yj[u] = py[j[u]]; zj[u] = pz[j[u]]; }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) nl_pair<MIC>(xi, yi, zi, xj[u], yj[u], zj[u], L, invL, rc2, fx, fy, fz, s12, s6);
+    const int ngrp = (cnt + 3) >> 2, nfull = cnt >> 2;
+    int4 j0 = make_int4(0, 0, 0, 0), j1 = j0;
+    if (ngrp > 0) j0 = __ldcs(nb);
+    if (ngrp > 1) j1 = __ldcs(nb + stride);
+    int g = 0;
+    for (; g < nfull; ++g) {
+        const int4 j = j0;
+        j0 = j1;
+        if (g + 2 < ngrp) j1 = __ldcs(nb + (size_t)(g + 2) * stride);
+        const double4 pa = nl_ld_pos(pos + j.x), pb = nl_ld_pos(pos + j.y), pc = nl_ld_pos(pos + j.z),
+                      pd = nl_ld_pos(pos + j.w);
+        nl_pair<MIC, false>(xi, yi, zi, pa, true, L, invL, rc2, fx, fy, fz, s12, s6);
+        nl_pair<MIC, false>(xi, yi, zi, pb, true, L, invL, rc2, fx, fy, fz, s12, s6);
+        nl_pair<MIC, false>(xi, yi, zi, pc, true, L, invL, rc2, fx, fy, fz, s12, s6);
+        nl_pair<MIC, false>(xi, yi, zi, pd, true, L, invL, rc2, fx, fy, fz, s12, s6);
     }
-    for (; m < cnt; ++m) {
-        const int j = __ldg(nb + (size_t)m * stride);
-        nl_pair<MIC>(xi, yi, zi, px[j], py[j], pz[j], L, invL, rc2, fx, fy, fz, s12, s6);
+    if (g < ngrp) { // last, partly filled group: padding entries point at the atom itself
+        const int rem = cnt & 3;
+        const double4 pa = nl_ld_pos(pos + j0.x), pb = nl_ld_pos(pos + j0.y), pc = nl_ld_pos(pos + j0.z);
+        nl_pair<MIC, true>(xi, yi, zi, pa, rem > 0, L, invL, rc2, fx, fy, fz, s12, s6);
+        nl_pair<MIC, true>(xi, yi, zi, pb, rem > 1, L, invL, rc2, fx, fy, fz, s12, s6);
+        nl_pair<MIC, true>(xi, yi, zi, pc, rem > 2, L, invL, rc2, fx, fy, fz, s12, s6);
     }
 }
 
@@ -364,21 +397,23 @@ __global__ void __launch_bounds__(NL_BS) nl_step_kernel(NlArgs a)
     const bool valid = i < n;
     const int cur = a.ctl->cur;
     const int ev = (MODE == 1) ? 1 - cur : cur;
-    const double *px = a.rb[ev], *py = px + n, *pz = py + n;
+    const double4 *pos = a.p4[ev];
     const double L = a.sc.L, invL = a.sc.invL, rc2 = a.sc.rc2;
 
     double xi = 0.0, yi = 0.0, zi = 0.0;
     int cnt = 0;
     bool inter = true;
     if (valid) {
-        xi = px[i]; yi = py[i]; zi = pz[i];
+        const double4 pi = nl_ld_pos(pos + i);
+        xi = pi.x; yi = pi.y; zi = pi.z;
         cnt = a.nb_cnt[i];
         inter = a.interior[i] != 0;
     }
     const bool fast = __all_sync(0xffffffffu, inter) && (a.ctl->unwrapped == 0);
     double fx = 0.0, fy = 0.0, fz = 0.0, s12 = 0.0, s6 = 0.0;
-    if (fast) nl_walk<false>(a.nbr + i, a.stride, cnt, px, py, pz, xi, yi, zi, L, invL, rc2, fx, fy, fz, s12, s6);
-    else nl_walk<true>(a.nbr + i, a.stride, cnt, px, py, pz, xi, yi, zi, L, invL, rc2, fx, fy, fz, s12, s6);
+    const int4 *nb = reinterpret_cast<const int4 *>(a.nbr) + i;
+    if (fast) nl_walk<false>(nb, a.stride, cnt, pos, xi, yi, zi, L, invL, rc2, fx, fy, fz, s12, s6);
+    else nl_walk<true>(nb, a.stride, cnt, pos, xi, yi, zi, L, invL, rc2, fx, fy, fz, s12, s6);
 
     double s[5] = {s12, s6, 0.0, 0.0, 0.0};
     double d2 = 0.0;
@@ -403,6 +438,7 @@ __global__ void __launch_bounds__(NL_BS) nl_step_kernel(NlArgs a)
             const double yn = nl_drift_wrap(yi, vy, ayn, a.sc);
             const double zn = nl_drift_wrap(zi, vz, azn, a.sc);
             pr[ix] = xn; pr[iy] = yn; pr[iz] = zn;
+            nl_st_pos(a.p4[cur] + i, xn, yn, zn);
             d2 = nl_disp2(a, i, xn, yn, zn);
         }
         a.a[ix] = axn; a.a[iy] = ayn; a.a[iz] = azn;
@@ -471,6 +507,7 @@ __global__ void __launch_bounds__(NL_BS) nl_drift_kernel(NlArgs a)
         const double yn = nl_drift_wrap(ps[iy], a.v[iy], a.a[iy], a.sc);
         const double zn = nl_drift_wrap(ps[iz], a.v[iz], a.a[iz], a.sc);
         pd[ix] = xn; pd[iy] = yn; pd[iz] = zn;
+        nl_st_pos(a.p4[1 - cur] + i, xn, yn, zn);
         d2 = nl_disp2(a, i, xn, yn, zn);
     }
     nl_block_max(d2, scratch, a.ctl);
@@ -528,7 +565,7 @@ __global__ void __launch_bounds__(NL_BS) nl_count_kernel(NlArgs a)
         const double xi = px[i], yi = py[i], zi = pz[i];
         const int cnt = a.nb_cnt[i];
         for (int m = 0; m < cnt; ++m) {
-            const int j = a.nbr[(size_t)m * a.stride + i];
+            const int j = a.nbr[nl_entry(a.stride, i, m)];
             const double dx = mic(xi - px[j], a.sc.L, a.sc.invL);
             const double dy = mic(yi - py[j], a.sc.L, a.sc.invL);
             const double dz = mic(zi - pz[j], a.sc.L, a.sc.invL);
@@ -574,6 +611,7 @@ static NlArgs make_args(ljmd_ctx *c, int eval_sel)
     a.rl2 = w.rl2; a.half_skin2 = w.half_skin2;
     a.maxnb = w.maxnb; a.stride = w.stride;
     a.rb[0] = c->rbuf[0]; a.rb[1] = c->rbuf[1];
+    a.p4[0] = w.p4; a.p4[1] = w.p4 + c->nR;
     a.v = c->st.vx; a.a = c->st.ax; a.ru = c->st.rux;
     a.r0 = w.r0; a.alt = w.alt;
     const size_t n = c->nR;
@@ -630,6 +668,8 @@ int nlist_plan(ljmd_ctx *c)
     LJMD_CUDA_CHECK(cudaMalloc(&w.interior, (size_t)n));
     LJMD_CUDA_CHECK(cudaMalloc(&w.nb_cnt, sizeof(int) * (size_t)n));
     LJMD_CUDA_CHECK(cudaMalloc(&w.nbr, sizeof(int) * w.stride * (size_t)w.maxnb));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.p4, sizeof(double4) * 2 * (size_t)n));
+    LJMD_CUDA_CHECK(cudaMemsetAsync(w.p4, 0, sizeof(double4) * 2 * (size_t)n, c->stream));
     LJMD_CUDA_CHECK(cudaMalloc(&w.r0, sizeof(double) * 3 * (size_t)n));
     LJMD_CUDA_CHECK(cudaMalloc(&w.alt, sizeof(double) * 15 * (size_t)n));
     LJMD_CUDA_CHECK(cudaMalloc(&w.spart, sizeof(double) * 5 * (size_t)w.nblk));
@@ -653,7 +693,7 @@ void nlist_free(ljmd_ctx *c)
     NlistWork &w = c->nw;
     cudaFree(w.cell_of_slot); cudaFree(w.cell_count); cudaFree(w.cell_start); cudaFree(w.cell_cursor);
     cudaFree(w.keys); cudaFree(w.orig); cudaFree(w.orig_alt); cudaFree(w.slot_of_orig); cudaFree(w.interior);
-    cudaFree(w.nb_cnt); cudaFree(w.nbr); cudaFree(w.r0); cudaFree(w.alt); cudaFree(w.spart); cudaFree(w.ctl);
+    cudaFree(w.nb_cnt); cudaFree(w.nbr); cudaFree(w.p4); cudaFree(w.r0); cudaFree(w.alt); cudaFree(w.spart); cudaFree(w.ctl);
     if (w.side_stream) cudaStreamDestroy(w.side_stream);
 }
 
@@ -938,7 +978,7 @@ extern "C" int ljmd_ctx_download_nlist(ljmd_ctx *c, int32_t *counts, int32_t *nb
         if (m > cap) return set_error(LJMD_ERR_ARG, "ljmd_ctx_download_nlist(): cap %d < %d neighbours.", cap, m);
         counts[o] = m;
         int32_t *dst = nbr + (size_t)o * cap;
-        for (int q = 0; q < m; ++q) dst[q] = h_orig[h_nbr[(size_t)q * w.stride + k]];
+        for (int q = 0; q < m; ++q) dst[q] = h_orig[h_nbr[nl_entry(w.stride, k, q)]];
         std::sort(dst, dst + m);
     }
     return LJMD_OK;

@@ -140,7 +140,7 @@ struct NlistWork {
     double scale;        // nc / L
     double skin, rl2, half_skin2;
     int maxnb;           // list capacity per atom
-    size_t stride;       // entry m of slot i is nbr[m*stride + i]
+    size_t stride;       // slots per entry group (n rounded up to 32); see nl_entry() in lj_nlist.cu
     int nblk, narr;
     int cur_host;        // host mirror of NlCtl::cur
     long long rebuilds_host, rebuilds_counted;
@@ -150,6 +150,7 @@ struct NlistWork {
     unsigned char *interior;
     int *nb_cnt, *nbr;
     double *r0, *alt, *spart;
+    double4 *p4;         // [2][n] packed positions (x, y, z, 0) of the two position buffers
     NlCtl *ctl;
     cudaStream_t side_stream; // captures the IF-node bodies of the step graph
 };
