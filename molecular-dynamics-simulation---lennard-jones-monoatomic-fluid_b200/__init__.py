@@ -26,7 +26,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libljmd.so")
+LIB_PATH = os.environ.get("LJMD_LIB_PATH") or os.path.join(_HERE, "lib", "libljmd.so")  # override: A/B builds
 
 METHOD_AUTO, METHOD_ALLPAIRS, METHOD_CELLS, METHOD_NLIST = 0, 1, 2, 3
 FLAG_TRACK_UNWRAPPED = 1

@@ -16,13 +16,22 @@
 //     device, no host round trip): cell id of every atom -> histogram (integer atomics) ->
 //     exclusive scan -> scatter -> per-cell sort by ORIGINAL index (= the stable counting sort,
 //     bit-exact against the CPU definition) -> permute all state arrays -> full neighbour list
-//     {j : |r_ij|_mic^2 < (rc+skin)^2}, stored transposed (entry m of slot i at nbr[m*stride+i])
-//     so that a warp reads 128 contiguous bytes per entry.
+//     {j : |r_ij|_mic^2 < (rc+skin)^2}.
+//     The list is stored in groups of four entries (one 16-byte load per thread), group g of all
+//     slots contiguous (a warp streams 512 contiguous bytes per group from HBM, read once).
+//     The build runs one CTA per work unit = (cell column, run of ~128 atoms along z) and stages
+//     the unit's neighbourhood (9 columns x z-window) in shared memory; the periodic image of a
+//     neighbour cell is a per-cell shift (exactly equal to the minimum image for every pair in
+//     range).
 //   * Step kernel: one thread per atom walks its list (ordered pairs: every thread accumulates
-//     only its own atom => no atomics, fixed summation order, bit-reproducible), gathers r_j from
-//     L1/L2, and finishes the velocity-Verlet step for its atom in the epilogue.  Warps whose atoms
-//     all sit in interior cells skip the minimum image (dx - L*0 = dx exactly); boundary warps use
-//     the rint() form.  The last CTA reduces the scalar partials in a fixed order.
+//     only its own atom => no atomics, fixed summation order, bit-reproducible), gathers the
+//     packed positions (x, y, z, 0: one 256-bit load = one 32-byte sector per neighbour) from
+//     L1/L2 and finishes the velocity-Verlet step for its atom in the epilogue.  Measured on
+//     B200 (profiles/): the gathers are bound by the L1 tag stage (~32 clocks per scattered warp
+//     gather); a variant that staged the neighbourhood in shared memory and kept 16-bit indices
+//     was slower (staging re-reads every position ~12x from L2).  Warps whose atoms all sit in interior
+//     cells skip the minimum image (dx - L*0 = dx exactly); boundary warps use the rint() form.
+//     The last CTA reduces the scalar partials in a fixed order.
 //   * Skin criterion (exact): a pair absent from the list had r > rc+skin at build time; while no
 //     atom has moved more than skin/2 it is still beyond rc.  The epilogue measures the displacement
 //     of the positions it just produced against the build positions.
@@ -39,7 +48,10 @@
 
 namespace ljmd {
 
-constexpr int NL_BS = 128; // threads per CTA of the per-atom kernels
+#ifndef NL_BS_VALUE
+#define NL_BS_VALUE 128
+#endif
+constexpr int NL_BS = NL_BS_VALUE; // threads per CTA (= target atoms per work unit) of the per-atom kernels
 
 // Kernel argument block (passed by value).
 struct NlArgs {
@@ -50,6 +62,8 @@ struct NlArgs {
     double half_skin2; // (skin/2)^2
     int maxnb;
     size_t stride;
+    int nzg, nunits;   // z-groups per column, work units (= CTAs of the build / step kernels)
+    int cap_stage;     // shared-memory staging capacity (atoms)
     double *rb[2];     // position buffers: x array; y, z follow at +n, +2n
     double4 *p4[2];    // the same positions packed (x, y, z, 0): one 32-byte sector per atom for the gathers
     double *v, *a;     // x arrays; y, z at +n, +2n
@@ -58,11 +72,12 @@ struct NlArgs {
     double *alt;       // [narr][n] permutation scratch
     double *arr[15];   // the state arrays that are permuted at a rebuild
     int narr;
-    int *cell_of_slot, *cell_count, *cell_start, *cell_cursor;
+    int *cell_of_slot, *cell_count, *cell_start, *cell_cursor, *tile_sum;
     unsigned long long *keys;
     int *orig, *orig_alt, *slot_of_orig;
     unsigned char *interior;
-    int *nb_cnt, *nbr;
+    int *nb_cnt;
+    int *nbr;          // the list: global slot indices, see nl_entry()
     NlCtl *ctl;
     StepCtl *sctl;
     double *spart; // [nblk][5]
@@ -132,24 +147,19 @@ __global__ void __launch_bounds__(256) nl_bin_kernel(NlArgs a)
     if (outside) a.ctl->unwrapped = 1;
 }
 
-// Exclusive scan, one CTA: every thread sums a contiguous run of cells, the run totals are scanned
-// in shared memory, then every thread writes its run.  Also re-arms the histogram and the cursors.
-__global__ void __launch_bounds__(1024) nl_scan_kernel(NlArgs a)
+// Exclusive scan of the histogram in three small kernels: (a) every CTA scans a tile of 1024 cells
+// and publishes the tile total, (b) one CTA scans the tile totals, (c) the tile offsets are added.
+// (a) also re-arms the histogram and the scatter cursors.
+__device__ __forceinline__ int nl_block_exscan(int v, int *wsum, int &total)
 {
-    if (!a.ctl->need_rebuild) return;
-    __shared__ int wsum[32];
-    const int ncells = a.ncells;
-    const int per = (ncells + 1023) / 1024;
-    const int b = threadIdx.x * per, e = min(ncells, b + per);
-    int s = 0;
-    for (int c = b; c < e; ++c) s += a.cell_count[c];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int x = s;
+    int x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int y = __shfl_up_sync(0xffffffffu, x, o);
         if (lane >= o) x += y;
     }
+    __syncthreads(); // wsum may still be read from a previous call
     if (lane == 31) wsum[warp] = x;
     __syncthreads();
     if (warp == 0) {
@@ -162,15 +172,43 @@ __global__ void __launch_bounds__(1024) nl_scan_kernel(NlArgs a)
         wsum[lane] = w;
     }
     __syncthreads();
-    int run = (warp > 0 ? wsum[warp - 1] : 0) + x - s; // exclusive prefix of this thread's run
-    for (int c = b; c < e; ++c) {
-        const int v = a.cell_count[c];
-        a.cell_start[c] = run;
-        a.cell_cursor[c] = 0;
-        a.cell_count[c] = 0;
-        run += v;
+    total = wsum[31];
+    return (warp > 0 ? wsum[warp - 1] : 0) + x - v;
+}
+
+__global__ void __launch_bounds__(1024) nl_scan_tiles_kernel(NlArgs a)
+{
+    if (!a.ctl->need_rebuild) return;
+    __shared__ int wsum[32];
+    const int c = blockIdx.x * 1024 + threadIdx.x;
+    const int v = c < a.ncells ? a.cell_count[c] : 0;
+    int total;
+    const int ex = nl_block_exscan(v, wsum, total);
+    if (c < a.ncells) { a.cell_start[c] = ex; a.cell_cursor[c] = 0; a.cell_count[c] = 0; }
+    if (threadIdx.x == 0) a.tile_sum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) nl_scan_sums_kernel(NlArgs a, int ntiles)
+{
+    if (!a.ctl->need_rebuild) return;
+    __shared__ int wsum[32];
+    int carry = 0;
+    for (int base = 0; base < ntiles; base += 1024) {
+        const int t = base + threadIdx.x;
+        const int v = t < ntiles ? a.tile_sum[t] : 0;
+        int total;
+        const int ex = nl_block_exscan(v, wsum, total);
+        if (t < ntiles) a.tile_sum[t] = carry + ex;
+        carry += total;
     }
-    if (threadIdx.x == 1023) a.cell_start[ncells] = wsum[31];
+    if (threadIdx.x == 0) a.cell_start[a.ncells] = carry;
+}
+
+__global__ void __launch_bounds__(1024) nl_scan_add_kernel(NlArgs a)
+{
+    if (!a.ctl->need_rebuild) return;
+    const int c = blockIdx.x * 1024 + threadIdx.x;
+    if (c < a.ncells) a.cell_start[c] += a.tile_sum[blockIdx.x];
 }
 
 __global__ void __launch_bounds__(256) nl_fill_kernel(NlArgs a)
@@ -220,63 +258,178 @@ __global__ void __launch_bounds__(256) nl_copyback_kernel(NlArgs a)
     if (k >= n) return;
     for (int q = 0; q < a.narr; ++q) a.arr[q][k] = a.alt[(size_t)q * n + k];
     a.orig[k] = a.orig_alt[k];
+    // packed copy of the positions the list is built for (arrays 0-2 are rb[0], 3-5 rb[1])
+    const int ev = a.ctl->cur ^ a.eval_sel;
+    nl_st_pos(a.p4[ev] + k, a.alt[(size_t)(3 * ev) * n + k], a.alt[(size_t)(3 * ev + 1) * n + k],
+              a.alt[(size_t)(3 * ev + 2) * n + k]);
 }
 
-// Full neighbour list of every slot from the 27-cell stencil (9 z-strips, contiguous in the
-// sorted order).  Membership is decided on r2 computed exactly like the reference computes it.
+// ------------------------------------------------------------------------------------------
+// Work units.  Unit u = (column col = u / nzg, z-group g = u % nzg) owns the cells
+// z0 = g*nc/nzg .. z1 = (g+1)*nc/nzg - 1 of its column: one contiguous slot range [ib, ie).  Its
+// neighbourhood is, for each of the 9 neighbour columns, the cells z0-1 .. z1+1 (periodic): one or
+// two contiguous slot runs.  Run r = 2*(column index) + piece is staged at shared-memory offset
+// off[r]; the same table is rebuilt from cell_start by the build kernel and by every step.
+// ------------------------------------------------------------------------------------------
+constexpr int NL_RUNS = 18;
+struct UnitTable {
+    int sb[NL_RUNS];      // first slot of the run
+    int off[NL_RUNS + 1]; // shared-memory offset of the run (prefix sum of the run lengths)
+    int za[NL_RUNS], zb[NL_RUNS]; // the run covers cells [za, zb) of its column
+    int ib, ie, cx, cy, z0, z1;
+};
+
+__device__ __forceinline__ void nl_unit_setup(const NlArgs &a, int unit, UnitTable &ut)
+{
+    const int nc = a.nc;
+    const int g = unit % a.nzg, col = unit / a.nzg;
+    const int cy = col % nc, cx = col / nc;
+    const int z0 = g * nc / a.nzg, z1 = (g + 1) * nc / a.nzg - 1;
+    __shared__ int len[NL_RUNS];
+    if (threadIdx.x < NL_RUNS) {
+        const int r = threadIdx.x, cidx = r >> 1, piece = r & 1;
+        const int nx = (cx + cidx / 3 - 1 + nc) % nc, ny = (cy + cidx % 3 - 1 + nc) % nc;
+        const int nb = (nx * nc + ny) * nc;
+        const int zlo = z0 - 1, zhi = z1 + 1;
+        int za = 0, zb = 0;
+        if (zhi - zlo + 1 >= nc) { if (!piece) { za = 0; zb = nc; } }              // whole column
+        else if (zlo < 0) { if (!piece) { za = nc - 1; zb = nc; } else { za = 0; zb = zhi + 1; } }
+        else if (zhi >= nc) { if (!piece) { za = zlo; zb = nc; } else { za = 0; zb = 1; } }
+        else { if (!piece) { za = zlo; zb = zhi + 1; } }
+        ut.za[r] = za; ut.zb[r] = zb;
+        const int s0 = a.cell_start[nb + za];
+        ut.sb[r] = s0;
+        len[r] = a.cell_start[nb + zb] - s0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int o = 0;
+        for (int r = 0; r < NL_RUNS; ++r) { ut.off[r] = o; o += len[r]; }
+        ut.off[NL_RUNS] = o;
+        const int cb = (cx * nc + cy) * nc;
+        ut.ib = a.cell_start[cb + z0];
+        ut.ie = a.cell_start[cb + z1 + 1];
+        ut.cx = cx; ut.cy = cy; ut.z0 = z0; ut.z1 = z1;
+    }
+    __syncthreads();
+}
+
+// Stage the neighbourhood positions: sx/sy/sz[q] for q in [0, off[NL_RUNS]).  Four independent
+// 256-bit loads per thread are in flight before the first shared-memory store.
+__device__ __forceinline__ void nl_stage(const UnitTable &ut, const double4 *__restrict__ pos, double *sx, double *sy,
+                                         double *sz, int total)
+{
+    constexpr int U = 4;
+    const int nt = blockDim.x;
+    int r = 0;
+    for (int q0 = threadIdx.x; q0 < total; q0 += U * nt) {
+        double4 p[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = q0 + u * nt;
+            if (q < total) {
+                while (q >= ut.off[r + 1]) ++r;
+                p[u] = nl_ld_pos(pos + (ut.sb[r] + q - ut.off[r]));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = q0 + u * nt;
+            if (q < total) { sx[q] = p[u].x; sy[q] = p[u].y; sz[q] = p[u].z; }
+        }
+    }
+}
+
+// Candidate test of the build: r2 in the reference's operation order (lj_potential_energy.f90:
+// 119-129).  With SHIFT the minimum image is the per-cell image shift k (dx - L*k, k in {-1,0,1},
+// the same single rounding as geometry_pbc.f90:86 for every pair in range); without it (unwrapped
+// input) the rint() form is used.
+template <bool SHIFT>
+__device__ __forceinline__ double nl_build_r2(double xi, double yi, double zi, double xj, double yj, double zj,
+                                              double sx_, double sy_, double sz_, double L, double invL)
+{
+    double dx = xi - xj, dy = yi - yj, dz = zi - zj;
+    if (SHIFT) { dx = dx - sx_; dy = dy - sy_; dz = dz - sz_; }
+    else { dx = mic(dx, L, invL); dy = mic(dy, L, invL); dz = mic(dz, L, invL); }
+    return dist2(dx, dy, dz);
+}
+
+template <bool STAGED, bool SHIFT>
+__device__ __forceinline__ int nl_build_atom(const NlArgs &a, const UnitTable &ut, const double4 *__restrict__ pos,
+                                             const double *sx, const double *sy, const double *sz, int i, double xi,
+                                             double yi, double zi, int cz)
+{
+    const int nc = a.nc;
+    const double L = a.sc.L, invL = a.sc.invL, rl2 = a.rl2;
+    int cnt = 0;
+    for (int cidx = 0; cidx < 9; ++cidx) {
+        const int ux = ut.cx + cidx / 3 - 1, uy = ut.cy + cidx % 3 - 1;
+        const int nx = (ux + nc) % nc, ny = (uy + nc) % nc;
+        const double shx = (ux < 0) ? -L : (ux >= nc) ? L : 0.0; // L * k, exact
+        const double shy = (uy < 0) ? -L : (uy >= nc) ? L : 0.0;
+        const int nb = (nx * nc + ny) * nc;
+        for (int w = cz - 1; w <= cz + 1; ++w) {
+            const int cw = (w + nc) % nc;
+            const double shz = (w < 0) ? -L : (w >= nc) ? L : 0.0;
+            const int s0 = a.cell_start[nb + cw], s1 = a.cell_start[nb + cw + 1];
+            int q0 = 0;
+            if (STAGED) {
+                const int r = 2 * cidx + ((cw >= ut.za[2 * cidx] && cw < ut.zb[2 * cidx]) ? 0 : 1);
+                q0 = ut.off[r] + (s0 - ut.sb[r]);
+            }
+            for (int k = 0; k < s1 - s0; ++k) {
+                double xj, yj, zj;
+                if (STAGED) { xj = sx[q0 + k]; yj = sy[q0 + k]; zj = sz[q0 + k]; }
+                else { const double4 pj = nl_ld_pos(pos + s0 + k); xj = pj.x; yj = pj.y; zj = pj.z; }
+                const double r2 = nl_build_r2<SHIFT>(xi, yi, zi, xj, yj, zj, shx, shy, shz, L, invL);
+                if (r2 < rl2 && (s0 + k) != i) {
+                    if (cnt < a.maxnb) a.nbr[nl_entry(a.stride, i, cnt)] = s0 + k;
+                    ++cnt;
+                }
+            }
+        }
+    }
+    return cnt;
+}
+
+// Full neighbour list of the unit's atoms.  Membership is decided on r2 computed exactly like the
+// reference computes it.  The unit's neighbourhood is staged in shared memory when it fits (it
+// does for any roughly homogeneous system); otherwise the candidates are read from global memory.
 __global__ void __launch_bounds__(NL_BS) nl_build_kernel(NlArgs a)
 {
     if (!a.ctl->need_rebuild) return;
+    extern __shared__ double smem[];
+    __shared__ UnitTable ut;
     const int n = a.sc.n, nc = a.nc;
-    const int i = blockIdx.x * NL_BS + threadIdx.x;
-    if (i < n) {
-        const double *px = a.rb[a.ctl->cur ^ a.eval_sel], *py = px + n, *pz = py + n;
-        const double L = a.sc.L, invL = a.sc.invL, rl2 = a.rl2;
-        const double xi = px[i], yi = py[i], zi = pz[i];
+    nl_unit_setup(a, blockIdx.x, ut);
+    const int total = ut.off[NL_RUNS];
+    const int ev = a.ctl->cur ^ a.eval_sel;
+    const double4 *pos = a.p4[ev];
+    double *sx = smem, *sy = sx + a.cap_stage, *sz = sy + a.cap_stage;
+    const bool staged = total <= a.cap_stage;
+    const bool shift = a.ctl->unwrapped == 0;
+    if (staged) nl_stage(ut, pos, sx, sy, sz, total);
+    __syncthreads();
+    const double L = a.sc.L, invL = a.sc.invL;
+    for (int i = ut.ib + threadIdx.x; i < ut.ie; i += NL_BS) {
+        const double4 pi = nl_ld_pos(pos + i);
+        const double xi = pi.x, yi = pi.y, zi = pi.z;
         bool outside = false;
-        const int cx = nl_cell_coord(xi, L, invL, a.scale, nc, outside);
-        const int cy = nl_cell_coord(yi, L, invL, a.scale, nc, outside);
         const int cz = nl_cell_coord(zi, L, invL, a.scale, nc, outside);
-        const int zlo = cz - 1, zhi = cz + 1;
-        const bool whole = (nc <= 3);
-        int cnt = 0;
-        for (int ox = -1; ox <= 1; ++ox) {
-            const int nx = (cx + ox + nc) % nc;
-            for (int oy = -1; oy <= 1; ++oy) {
-                const int ny = (cy + oy + nc) % nc;
-                const int base = (nx * nc + ny) * nc;
-                int sb[2], se[2], npieces;
-                if (whole) {
-                    sb[0] = a.cell_start[base]; se[0] = a.cell_start[base + nc]; npieces = 1;
-                } else if (zlo < 0) {
-                    sb[0] = a.cell_start[base + nc - 1]; se[0] = a.cell_start[base + nc];
-                    sb[1] = a.cell_start[base]; se[1] = a.cell_start[base + zhi + 1]; npieces = 2;
-                } else if (zhi >= nc) {
-                    sb[0] = a.cell_start[base + zlo]; se[0] = a.cell_start[base + nc];
-                    sb[1] = a.cell_start[base]; se[1] = a.cell_start[base + 1]; npieces = 2;
-                } else {
-                    sb[0] = a.cell_start[base + zlo]; se[0] = a.cell_start[base + zhi + 1]; npieces = 1;
-                }
-                for (int pc = 0; pc < npieces; ++pc) {
-                    for (int j = sb[pc]; j < se[pc]; ++j) {
-                        const double dx = mic(xi - px[j], L, invL);
-                        const double dy = mic(yi - py[j], L, invL);
-                        const double dz = mic(zi - pz[j], L, invL);
-                        const double r2 = dist2(dx, dy, dz);
-                        if (r2 < rl2 && j != i) {
-                            if (cnt < a.maxnb) a.nbr[nl_entry(a.stride, i, cnt)] = j;
-                            ++cnt;
-                        }
-                    }
-                }
-            }
+        int cnt;
+        if (staged) {
+            if (shift) cnt = nl_build_atom<true, true>(a, ut, pos, sx, sy, sz, i, xi, yi, zi, cz);
+            else cnt = nl_build_atom<true, false>(a, ut, pos, sx, sy, sz, i, xi, yi, zi, cz);
+        } else {
+            if (shift) cnt = nl_build_atom<false, true>(a, ut, pos, sx, sy, sz, i, xi, yi, zi, cz);
+            else cnt = nl_build_atom<false, false>(a, ut, pos, sx, sy, sz, i, xi, yi, zi, cz);
         }
         if (cnt > a.maxnb) atomicMax(&a.ctl->overflow, cnt);
         cnt = min(cnt, a.maxnb);
         a.nb_cnt[i] = cnt;
         for (int m = cnt; m & 3; ++m) a.nbr[nl_entry(a.stride, i, m)] = i; // pad the last group (masked in the walk)
-        nl_st_pos(a.p4[a.ctl->cur ^ a.eval_sel] + i, xi, yi, zi);
         a.r0[i] = xi; a.r0[(size_t)n + i] = yi; a.r0[2 * (size_t)n + i] = zi;
+        const int cx = ut.cx, cy = ut.cy;
         const bool inter = cx >= 1 && cx <= nc - 2 && cy >= 1 && cy <= nc - 2 && cz >= 1 && cz <= nc - 2;
         a.interior[i] = inter ? 1 : 0;
     }
@@ -317,8 +470,10 @@ __device__ __forceinline__ void nl_pair(double xi, double yi, double zi, const d
     fx = fma(g, dx, fx); fy = fma(g, dy, fy); fz = fma(g, dz, fz);
 }
 
-// Walk of one atom's list.  The index groups stream from HBM (read once: cache-streaming loads,
-// prefetched two groups ahead); the packed positions are gathered from L1/L2.
+// Walk of one atom's list.  The index groups stream from HBM (read once: cache-streaming loads, a
+// ring of NL_PF groups is kept in flight); the packed positions are gathered from L1/L2.
+constexpr int NL_PF = 3;
+
 template <bool MIC>
 __device__ __forceinline__ void nl_walk(const int4 *__restrict__ nb, size_t stride, int cnt,
                                         const double4 *__restrict__ pos, double xi, double yi, double zi, double L,
@@ -326,14 +481,18 @@ __device__ __forceinline__ void nl_walk(const int4 *__restrict__ nb, size_t stri
                                         double &s6)
 {
     const int ngrp = (cnt + 3) >> 2, nfull = cnt >> 2;
-    int4 j0 = make_int4(0, 0, 0, 0), j1 = j0;
-    if (ngrp > 0) j0 = __ldcs(nb);
-    if (ngrp > 1) j1 = __ldcs(nb + stride);
+    int4 ring[NL_PF];
+#pragma unroll
+    for (int u = 0; u < NL_PF; ++u) {
+        ring[u] = make_int4(0, 0, 0, 0);
+        if (u < ngrp) ring[u] = __ldcs(nb + (size_t)u * stride);
+    }
     int g = 0;
     for (; g < nfull; ++g) {
-        const int4 j = j0;
-        j0 = j1;
-        if (g + 2 < ngrp) j1 = __ldcs(nb + (size_t)(g + 2) * stride);
+        const int4 j = ring[0];
+#pragma unroll
+        for (int u = 0; u + 1 < NL_PF; ++u) ring[u] = ring[u + 1];
+        if (g + NL_PF < ngrp) ring[NL_PF - 1] = __ldcs(nb + (size_t)(g + NL_PF) * stride);
         const double4 pa = nl_ld_pos(pos + j.x), pb = nl_ld_pos(pos + j.y), pc = nl_ld_pos(pos + j.z),
                       pd = nl_ld_pos(pos + j.w);
         nl_pair<MIC, false>(xi, yi, zi, pa, true, L, invL, rc2, fx, fy, fz, s12, s6);
@@ -341,9 +500,10 @@ __device__ __forceinline__ void nl_walk(const int4 *__restrict__ nb, size_t stri
         nl_pair<MIC, false>(xi, yi, zi, pc, true, L, invL, rc2, fx, fy, fz, s12, s6);
         nl_pair<MIC, false>(xi, yi, zi, pd, true, L, invL, rc2, fx, fy, fz, s12, s6);
     }
-    if (g < ngrp) { // last, partly filled group: padding entries point at the atom itself
+    if (g < ngrp) { // last, partly filled group: padding entries point at the atom itself and are masked
+        const int4 j = ring[0];
         const int rem = cnt & 3;
-        const double4 pa = nl_ld_pos(pos + j0.x), pb = nl_ld_pos(pos + j0.y), pc = nl_ld_pos(pos + j0.z);
+        const double4 pa = nl_ld_pos(pos + j.x), pb = nl_ld_pos(pos + j.y), pc = nl_ld_pos(pos + j.z);
         nl_pair<MIC, true>(xi, yi, zi, pa, rem > 0, L, invL, rc2, fx, fy, fz, s12, s6);
         nl_pair<MIC, true>(xi, yi, zi, pb, rem > 1, L, invL, rc2, fx, fy, fz, s12, s6);
         nl_pair<MIC, true>(xi, yi, zi, pc, rem > 2, L, invL, rc2, fx, fy, fz, s12, s6);
@@ -610,6 +770,7 @@ static NlArgs make_args(ljmd_ctx *c, int eval_sel)
     a.nc = w.nc; a.ncells = w.ncells; a.scale = w.scale;
     a.rl2 = w.rl2; a.half_skin2 = w.half_skin2;
     a.maxnb = w.maxnb; a.stride = w.stride;
+    a.nzg = w.nzg; a.nunits = w.nunits; a.cap_stage = w.cap_stage;
     a.rb[0] = c->rbuf[0]; a.rb[1] = c->rbuf[1];
     a.p4[0] = w.p4; a.p4[1] = w.p4 + c->nR;
     a.v = c->st.vx; a.a = c->st.ax; a.ru = c->st.rux;
@@ -623,7 +784,7 @@ static NlArgs make_args(ljmd_ctx *c, int eval_sel)
     a.narr = q;
     for (; q < 15; ++q) a.arr[q] = nullptr;
     a.cell_of_slot = w.cell_of_slot; a.cell_count = w.cell_count; a.cell_start = w.cell_start;
-    a.cell_cursor = w.cell_cursor; a.keys = w.keys;
+    a.cell_cursor = w.cell_cursor; a.tile_sum = w.tile_sum; a.keys = w.keys;
     a.orig = w.orig; a.orig_alt = w.orig_alt; a.slot_of_orig = w.slot_of_orig;
     a.interior = w.interior; a.nb_cnt = w.nb_cnt; a.nbr = w.nbr;
     a.ctl = w.ctl; a.sctl = c->fw.ctl;
@@ -656,11 +817,27 @@ int nlist_plan(ljmd_ctx *c)
     w.stride = ((size_t)n + 31) / 32 * 32;
     w.nblk = (n + NL_BS - 1) / NL_BS;
     w.narr = c->st.rux ? 15 : 12;
+    // work units: runs of about NL_BS atoms along z inside one cell column
+    const double apc = (double)n / w.ncells; // atoms per cell
+    int G = (int)floor((double)NL_BS / apc);
+    G = std::max(1, std::min(G, w.nc));
+    w.nzg = (w.nc + G - 1) / G;
+    w.nunits = w.nc * w.nc * w.nzg;
+    const int gmax = (w.nc + w.nzg - 1) / w.nzg; // cells of the longest z-group
+    int cap_stage = (int)(1.2 * 9.0 * std::min(w.nc, gmax + 2) * apc) + 96;
+    if (const char *e = getenv("LJMD_NL_STAGE")) cap_stage = atoi(e);
+    cap_stage = std::min(cap_stage, 9300); // 3 x 8 bytes per atom, 227 KB of shared memory per CTA
+    cap_stage = std::min(cap_stage, 65535);
+    w.cap_stage = (cap_stage + 15) / 16 * 16;
+    w.smem_bytes = sizeof(double) * 3 * (size_t)w.cap_stage;
+    LJMD_CUDA_CHECK(cudaFuncSetAttribute(nl_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem_bytes));
+
     w.cur_host = 0;
     LJMD_CUDA_CHECK(cudaMalloc(&w.cell_of_slot, sizeof(int) * (size_t)n));
     LJMD_CUDA_CHECK(cudaMalloc(&w.cell_count, sizeof(int) * (size_t)w.ncells));
     LJMD_CUDA_CHECK(cudaMalloc(&w.cell_start, sizeof(int) * ((size_t)w.ncells + 1)));
     LJMD_CUDA_CHECK(cudaMalloc(&w.cell_cursor, sizeof(int) * (size_t)w.ncells));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.tile_sum, sizeof(int) * (size_t)((w.ncells + 1023) / 1024)));
     LJMD_CUDA_CHECK(cudaMalloc(&w.keys, sizeof(unsigned long long) * (size_t)n));
     LJMD_CUDA_CHECK(cudaMalloc(&w.orig, sizeof(int) * (size_t)n));
     LJMD_CUDA_CHECK(cudaMalloc(&w.orig_alt, sizeof(int) * (size_t)n));
@@ -691,7 +868,7 @@ int nlist_plan(ljmd_ctx *c)
 void nlist_free(ljmd_ctx *c)
 {
     NlistWork &w = c->nw;
-    cudaFree(w.cell_of_slot); cudaFree(w.cell_count); cudaFree(w.cell_start); cudaFree(w.cell_cursor);
+    cudaFree(w.cell_of_slot); cudaFree(w.cell_count); cudaFree(w.cell_start); cudaFree(w.cell_cursor); cudaFree(w.tile_sum);
     cudaFree(w.keys); cudaFree(w.orig); cudaFree(w.orig_alt); cudaFree(w.slot_of_orig); cudaFree(w.interior);
     cudaFree(w.nb_cnt); cudaFree(w.nbr); cudaFree(w.p4); cudaFree(w.r0); cudaFree(w.alt); cudaFree(w.spart); cudaFree(w.ctl);
     if (w.side_stream) cudaStreamDestroy(w.side_stream);
@@ -722,13 +899,16 @@ int nlist_enqueue_rebuild(ljmd_ctx *c, int eval_sel)
     const int n = c->sc.n;
     const NlArgs a = make_args(c, eval_sel);
     nl_bin_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(a);
-    nl_scan_kernel<<<1, 1024, 0, c->stream>>>(a);
+    const int ntiles = (w.ncells + 1023) / 1024;
+    nl_scan_tiles_kernel<<<ntiles, 1024, 0, c->stream>>>(a);
+    nl_scan_sums_kernel<<<1, 1024, 0, c->stream>>>(a, ntiles);
+    nl_scan_add_kernel<<<ntiles, 1024, 0, c->stream>>>(a);
     nl_fill_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(a);
     nl_sortcell_kernel<<<(w.ncells + 127) / 128, 128, 0, c->stream>>>(a);
     nl_permute_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(a);
     nl_copyback_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(a);
-    nl_build_kernel<<<w.nblk, NL_BS, 0, c->stream>>>(a);
-    if (!c->capturing) c->launches += 7;
+    nl_build_kernel<<<w.nunits, NL_BS, w.smem_bytes, c->stream>>>(a);
+    if (!c->capturing) c->launches += 9;
     LJMD_CUDA_CHECK(cudaGetLastError());
     return LJMD_OK;
 }

@@ -232,8 +232,8 @@ static int fetch_obs(ljmd_ctx *c, double *dst, int per_rep, const int *idx)
             for (int k = 0; k < per_rep; ++k) dst[(size_t)r * per_rep + k] = c->h_obs[4 * r + idx[k]];
     if (c->method == LJMD_METHOD_NLIST) {
         LJMD_TRY(nlist_check_overflow(c));
-        // list builds that ran inside graph IF nodes: 7 kernels each
-        if (c->graph_chunk) c->launches += 7 * (c->nw.rebuilds_host - c->nw.rebuilds_counted);
+        // list builds that ran inside graph IF nodes: 9 kernels each
+        if (c->graph_chunk) c->launches += 9 * (c->nw.rebuilds_host - c->nw.rebuilds_counted);
         c->nw.rebuilds_counted = c->nw.rebuilds_host;
     }
     return LJMD_OK;

@@ -144,11 +144,14 @@ struct NlistWork {
     int nblk, narr;
     int cur_host;        // host mirror of NlCtl::cur
     long long rebuilds_host, rebuilds_counted;
-    int *cell_of_slot, *cell_count, *cell_start, *cell_cursor;
+    int *cell_of_slot, *cell_count, *cell_start, *cell_cursor, *tile_sum;
     unsigned long long *keys;
     int *orig, *orig_alt, *slot_of_orig;
     unsigned char *interior;
-    int *nb_cnt, *nbr;
+    int *nb_cnt;
+    int *nbr;              // the list (global slot indices, groups of four)
+    int nzg, nunits, cap_stage;
+    size_t smem_bytes;
     double *r0, *alt, *spart;
     double4 *p4;         // [2][n] packed positions (x, y, z, 0) of the two position buffers
     NlCtl *ctl;
