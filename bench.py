@@ -186,6 +186,62 @@ def run_reference(args, w, wname):
     print(json.dumps(line), flush=True)
 
 
+def run_slabs(args, w, lj, mg, dist, rank, world, local, n, arrs, p):
+    """Strong scaling of ONE large system with the neighbour-list path: slab sharding in the
+    cell-sorted order, halo positions pushed into peer memory by the step kernel itself, per-step
+    flags instead of collectives; NCCL only for the all-gather at list rebuilds."""
+    import torch
+    dev = torch.device("cuda", local)
+    ctx = lj.Context(p, method=lj.METHOD_NLIST, device=local)
+    ctx.upload(lj.SimState.from_arrays(arrs))
+    ctx.compute_forces()
+    runner = mg.SlabRunner(ctx, rank, world, chunk=32)
+    runner.step(args.warmup)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0, r0 = ctx.launch_count, runner.rebuilds
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    share = runner.step(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    launches = ctx.launch_count - l0
+    clocks = sampler.finish()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed = float(t.item())
+    obs = mg.reduce_observables(torch.tensor(share, dtype=torch.float64, device=dev), lj.tail_corrections(p))
+    if not np.all(np.isfinite(obs)):
+        raise SystemExit(f"bench.py: non-finite observables {obs}")
+    info = ctx.nlist_info()
+    if rank == 0:
+        line = {
+            "metric": "atom_steps_per_s", "value": n * args.steps / elapsed, "unit": "atom-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "n_atoms": n, "box_length": w["L"], "rc": w["rc"], "dt": w["dt"],
+                       "method": "nlist", "skin": info["skin"],
+                       "multi_gpu": "slabs of cell layers in the cell-sorted order; boundary-layer positions written "
+                                    "into the neighbour ranks' buffers by the step kernel (peer memory over NVLink), "
+                                    "per-step flags, no collective per step; NCCL all-gather of the state only at list "
+                                    "rebuilds (%d in the timed region)" % (runner.rebuilds - r0),
+                       "l2": "state %.0f MB per GPU (> L2 with the neighbour list: %.0f MB)" %
+                             (96 * n / 1e6, 4 * info["entries"] / 1e6 / world)},
+            "roofline": None, "cpu_baseline": None, "e2e": None, "clocks": clocks,
+            "gpu_launches": int(launches * world), "wall_s": wall,
+            "obs_last": [float(x) for x in obs],
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def run_sharded(args, w, lj, dist, rank, world, local, n, arrs, p):
     """Strong scaling of ONE large system (cell list) over the ranks: i-particle-range sharding,
     NCCL all-gather of the positions every step, observables reduced in rank order."""
@@ -194,6 +250,8 @@ def run_sharded(args, w, lj, dist, rank, world, local, n, arrs, p):
     import torch
     mg = importlib.import_module(lj.__name__ + ".multi_gpu")
     dev = torch.device("cuda", local)
+    if w["method"] == "nlist":
+        return run_slabs(args, w, lj, mg, dist, rank, world, local, n, arrs, p)
     ctx = lj.Context(p, method=lj.METHOD_CELLS, device=local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.upload(lj.SimState.from_arrays(arrs))
@@ -288,7 +346,7 @@ def main():
     if lj.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
 
-    sharded = world > 1 and w["method"] == "cells"
+    sharded = world > 1 and w["method"] in ("cells", "nlist")
     n, arrs = synthetic_state(w, seed=0 if sharded else rank)
     p = lj.init_params(n, w["L"], w["dt"], w["rc"], w["k"])
     method = {"cells": lj.METHOD_CELLS, "nlist": lj.METHOD_NLIST}.get(w["method"], lj.METHOD_ALLPAIRS)

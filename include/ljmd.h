@@ -188,6 +188,37 @@ int ljmd_ctx_shard_end(ljmd_ctx *ctx);
 /* Tail corrections of lj_potential_energy.f90:205-223 (added once after a cross-rank reduction). */
 int ljmd_tail_corrections(const ljmd_params *params, double *tail_epot, double *tail_d_epot,
                           double *tail_dd_epot);
+/* ---- Slab sharding of the neighbour-list path (LJMD_METHOD_NLIST) over the GPUs of one node.
+ * The cell-sorted slot order makes contiguous slot ranges spatial slabs: rank r owns the cell
+ * layers cx in [r*nc/world, (r+1)*nc/world).  Every step kernel writes the new positions of its
+ * boundary layers straight into the neighbour ranks' position buffers (peer memory over NVLink)
+ * and publishes a per-step flag to every rank; the next step starts when all flags have arrived
+ * (no host round trip, no NCCL call per step).  A skin violation on any rank halts all ranks at
+ * the same step; the host then gathers the complete state (one NCCL all-gather of the packed
+ * slabs), and every rank re-sorts and rebuilds the lists of its own slab.
+ *   export  : 128 bytes = two cudaIpcMemHandle_t (position buffers, flag block) and/or the raw
+ *             device pointers (for contexts living in the same process)
+ *   attach  : all_handles = world x 128 bytes in rank order (or all_raw_ptrs = world x 2) */
+#define LJMD_MAX_RANKS 8
+int ljmd_ctx_slab_export(ljmd_ctx *ctx, void *handles128, uint64_t *raw_ptrs2);
+int ljmd_ctx_slab_attach(ljmd_ctx *ctx, int32_t rank, int32_t world, const void *all_handles,
+                         const uint64_t *all_raw_ptrs);
+/* First slot of every rank's slab in the current sorted order; bounds[world] = n. */
+int ljmd_ctx_slab_bounds(ljmd_ctx *ctx, int32_t *bounds);
+/* Owned range of every state array -> dense device buffer [narr][cmax] (dev_buf NULL: query narr). */
+int ljmd_ctx_slab_pack(ljmd_ctx *ctx, double *dev_buf, int32_t cmax, int32_t *narr);
+/* All ranks' packed ranges [world][narr][cmax] -> state arrays: the complete state on this rank. */
+int ljmd_ctx_slab_unpack(ljmd_ctx *ctx, const double *dev_buf, int32_t cmax);
+/* r(t+dt) of all atoms from the complete state (start of a sharded run). */
+int ljmd_ctx_slab_drift(ljmd_ctx *ctx);
+/* Global re-sort + list rebuild for the next step's positions (needs the complete state) if a
+ * halt / the skin check asked for it or force != 0; clears the halt. */
+int ljmd_ctx_slab_rebuild(ljmd_ctx *ctx, int32_t force);
+/* Up to max_steps steps; *halted != 0 => gather (pack / all-gather / unpack) + rebuild, then go on.
+ * obs4 = this rank's share of {epot, ekin, d_epot, dd_epot} of the last step, no tail corrections. */
+int ljmd_ctx_slab_run(ljmd_ctx *ctx, int32_t max_steps, int32_t *steps_done, int32_t *halted,
+                      double *obs4);
+
 /* Tuning aid: per-warp {start, end, smid, items} clock records of the last independent-warp
  * all-pairs launch (context created with LJMD_SYM_DEBUG=1); returns the number of warps. */
 int ljmd_ctx_debug_warp_times(ljmd_ctx *ctx, long long *out, int max_warps);

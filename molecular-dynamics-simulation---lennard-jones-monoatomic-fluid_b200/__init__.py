@@ -88,7 +88,10 @@ ABI_SYMBOLS = [
     "ljmd_ctx_set_stream", "ljmd_ctx_device_ptrs", "ljmd_ctx_set_shard", "ljmd_ctx_shard_begin",
     "ljmd_ctx_shard_step", "ljmd_ctx_shard_end", "ljmd_tail_corrections", "ljmd_ctx_debug_warp_times",
     "ljmd_ctx_nlist_info", "ljmd_ctx_download_nlist",
+    "ljmd_ctx_slab_export", "ljmd_ctx_slab_attach", "ljmd_ctx_slab_bounds", "ljmd_ctx_slab_pack",
+    "ljmd_ctx_slab_unpack", "ljmd_ctx_slab_drift", "ljmd_ctx_slab_rebuild", "ljmd_ctx_slab_run",
 ]
+MAX_RANKS = 8
 
 
 def load_library() -> C.CDLL:
@@ -383,6 +386,56 @@ class Context:
         _chk(self._L.ljmd_ctx_download_nlist(self._h, counts.ctypes.data_as(_IP),
                                              nbr.ctypes.data_as(_IP), cap))
         return counts, nbr
+
+    # ---- slab sharding of the neighbour-list path (see include/ljmd.h) ------------------------
+    def slab_export(self):
+        """(128-byte IPC handle blob, (p4_ptr, flags_ptr))"""
+        h = (C.c_ubyte * 128)()
+        raw = (C.c_uint64 * 2)()
+        _chk(self._L.ljmd_ctx_slab_export(self._h, h, raw))
+        return bytes(h), (int(raw[0]), int(raw[1]))
+
+    def slab_attach(self, rank: int, world: int, handles=None, raw_ptrs=None) -> None:
+        hb = None
+        if handles is not None:
+            blob = b"".join(handles)
+            assert len(blob) == 128 * world
+            hb = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        rp = None
+        if raw_ptrs is not None:
+            flat = [int(x) for pair in raw_ptrs for x in pair]
+            rp = (C.c_uint64 * len(flat))(*flat)
+        _chk(self._L.ljmd_ctx_slab_attach(self._h, int(rank), int(world), hb, rp))
+        self._slab_world = world
+
+    def slab_bounds(self) -> np.ndarray:
+        b = np.zeros(self._slab_world + 1, dtype=np.int32)
+        _chk(self._L.ljmd_ctx_slab_bounds(self._h, b.ctypes.data_as(_IP)))
+        return b
+
+    def slab_narr(self) -> int:
+        k = C.c_int32()
+        _chk(self._L.ljmd_ctx_slab_pack(self._h, None, 0, C.byref(k)))
+        return k.value
+
+    def slab_pack(self, dev_ptr: int, cmax: int) -> None:
+        _chk(self._L.ljmd_ctx_slab_pack(self._h, C.c_void_p(dev_ptr), int(cmax), None))
+
+    def slab_unpack(self, dev_ptr: int, cmax: int) -> None:
+        _chk(self._L.ljmd_ctx_slab_unpack(self._h, C.c_void_p(dev_ptr), int(cmax)))
+
+    def slab_drift(self) -> None:
+        _chk(self._L.ljmd_ctx_slab_drift(self._h))
+
+    def slab_rebuild(self, force: bool = False) -> None:
+        _chk(self._L.ljmd_ctx_slab_rebuild(self._h, 1 if force else 0))
+
+    def slab_run(self, max_steps: int):
+        """(steps_done, halted, obs_share[4])"""
+        done, halted = C.c_int32(), C.c_int32()
+        obs = np.zeros(4)
+        _chk(self._L.ljmd_ctx_slab_run(self._h, int(max_steps), C.byref(done), C.byref(halted), _p(obs)))
+        return done.value, bool(halted.value), obs
 
     def download_cells(self):
         nc = self.cells_per_edge

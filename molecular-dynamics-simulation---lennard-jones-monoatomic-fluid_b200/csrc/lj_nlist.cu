@@ -83,6 +83,11 @@ struct NlArgs {
     double *spart; // [nblk][5]
     int nblk;
     double *obs;   // [4]
+    // ---- slab sharding over GPUs (sh_on): this rank owns the cell layers cx in [xlo, xhi)
+    int sh_on, rank, world, xlo, xhi;
+    double4 *peer_p4[LJMD_MAX_RANKS]; // p4 base ([2][n]) of every rank, mapped into this process
+    int *peer_flags[LJMD_MAX_RANKS];  // flag block ([2][LJMD_MAX_RANKS] ints) of every rank
+    int *flags;                       // this rank's flag block (the peers write into it)
     int eval_sel;  // rebuild kernels: 0 = the list is for rb[cur], 1 = for rb[1-cur]
     unsigned long long *pair_counts;
 };
@@ -401,17 +406,20 @@ __global__ void __launch_bounds__(NL_BS) nl_build_kernel(NlArgs a)
     extern __shared__ double smem[];
     __shared__ UnitTable ut;
     const int n = a.sc.n, nc = a.nc;
-    nl_unit_setup(a, blockIdx.x, ut);
-    const int total = ut.off[NL_RUNS];
+    // sharded: only the units of the owned cell layers get lists (the sort above covered all atoms)
+    const int ucx = (int)(blockIdx.x / a.nzg) / nc;
+    const bool mine = !a.sh_on || (ucx >= a.xlo && ucx < a.xhi);
+    if (mine) nl_unit_setup(a, blockIdx.x, ut);
+    const int total = mine ? ut.off[NL_RUNS] : 0;
     const int ev = a.ctl->cur ^ a.eval_sel;
     const double4 *pos = a.p4[ev];
     double *sx = smem, *sy = sx + a.cap_stage, *sz = sy + a.cap_stage;
     const bool staged = total <= a.cap_stage;
     const bool shift = a.ctl->unwrapped == 0;
-    if (staged) nl_stage(ut, pos, sx, sy, sz, total);
+    if (mine && staged) nl_stage(ut, pos, sx, sy, sz, total);
     __syncthreads();
     const double L = a.sc.L, invL = a.sc.invL;
-    for (int i = ut.ib + threadIdx.x; i < ut.ie; i += NL_BS) {
+    for (int i = (mine ? ut.ib : 0) + threadIdx.x; i < (mine ? ut.ie : 0); i += NL_BS) {
         const double4 pi = nl_ld_pos(pos + i);
         const double xi = pi.x, yi = pi.y, zi = pi.z;
         bool outside = false;
@@ -547,14 +555,65 @@ __device__ __forceinline__ void nl_block_max(double d2, double *scratch, NlCtl *
 // MODE 1: one verlet_step: forces at rb[1-cur] (already drifted), both half kicks, E_kin,
 // unwrapped update, r(t+2dt) -> rb[cur], skin check; the last CTA flips cur.
 // ------------------------------------------------------------------------------------------
-template <int MODE, bool TRACK>
+__device__ __forceinline__ int nl_ld_acquire_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void nl_st_release_sys(int *p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// SH (slab sharding, MODE 1 only): the kernel handles the slots of the owned cell layers.  Step s+1
+// starts only when every rank has published its flag of step s (value = (s << 1) | violated, in
+// the parity slot s & 1 of this rank's flag block): at that point the halo positions written by
+// the neighbours into p4 are visible, and nobody still reads the buffer this step overwrites.  If
+// any rank reported a skin violation the kernel halts (no state change) until the host has
+// re-gathered the state and rebuilt the lists.
+template <int MODE, bool TRACK, bool SH>
 __global__ void __launch_bounds__(NL_BS) nl_step_kernel(NlArgs a)
 {
     __shared__ double scratch[5 * (NL_BS / 32)];
     __shared__ bool is_last;
+    __shared__ int s_viol;
     const int n = a.sc.n;
-    const int i = blockIdx.x * NL_BS + threadIdx.x;
-    const bool valid = i < n;
+    int i = blockIdx.x * NL_BS + threadIdx.x;
+    bool valid = i < n;
+    int nact = gridDim.x, seq = 0, sb = 0, se = n;
+    if (SH) {
+        if (a.ctl->halted || a.ctl->steps_left <= 0) return;
+        seq = a.ctl->seq;
+        if (threadIdx.x == 0) {
+            int viol = 0;
+            if (seq > 0) {
+                const int *f = a.flags + (seq & 1) * LJMD_MAX_RANKS;
+                for (int q = 0; q < a.world; ++q) {
+                    int v;
+                    while (((v = nl_ld_acquire_sys(f + q)) >> 1) < seq) __nanosleep(40);
+                    viol |= v & 1;
+                }
+            }
+            s_viol = viol;
+        }
+        __syncthreads();
+        if (s_viol) { // some atom moved more than skin/2: the list may be stale for this step
+            if (blockIdx.x == 0 && threadIdx.x == 0) { a.ctl->halted = 1; a.ctl->need_rebuild = 1; }
+            return;
+        }
+        const int layer = a.nc * a.nc;
+        sb = a.cell_start[a.xlo * layer];
+        se = a.cell_start[a.xhi * layer];
+        nact = (se - sb + NL_BS - 1) / NL_BS;
+        if (nact > (int)gridDim.x) { // more owned atoms than the launch has CTAs for: flagged, reported by the host
+            if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(&a.ctl->overflow, 0x40000000);
+            nact = gridDim.x;
+        }
+        if ((int)blockIdx.x >= nact) return;
+        i = sb + blockIdx.x * NL_BS + threadIdx.x;
+        valid = i < se;
+    }
     const int cur = a.ctl->cur;
     const int ev = (MODE == 1) ? 1 - cur : cur;
     const double4 *pos = a.p4[ev];
@@ -599,6 +658,19 @@ __global__ void __launch_bounds__(NL_BS) nl_step_kernel(NlArgs a)
             const double zn = nl_drift_wrap(zi, vz, azn, a.sc);
             pr[ix] = xn; pr[iy] = yn; pr[iz] = zn;
             nl_st_pos(a.p4[cur] + i, xn, yn, zn);
+            if (SH) {
+                // halo push over NVLink: the first / last owned cell layer is the neighbour ranks' halo
+                const int layer = a.nc * a.nc;
+                const size_t off = (size_t)cur * n + i;
+                if (i < a.cell_start[(a.xlo + 1) * layer]) {
+                    const int left = (a.rank + a.world - 1) % a.world;
+                    if (left != a.rank) nl_st_pos(a.peer_p4[left] + off, xn, yn, zn);
+                }
+                if (i >= a.cell_start[(a.xhi - 1) * layer]) {
+                    const int right = (a.rank + 1) % a.world;
+                    if (right != a.rank) nl_st_pos(a.peer_p4[right] + off, xn, yn, zn);
+                }
+            }
             d2 = nl_disp2(a, i, xn, yn, zn);
         }
         a.a[ix] = axn; a.a[iy] = ayn; a.a[iz] = azn;
@@ -606,13 +678,14 @@ __global__ void __launch_bounds__(NL_BS) nl_step_kernel(NlArgs a)
     }
     block_sum<5>(s, scratch);
     if (MODE == 1) nl_block_max(d2, scratch, a.ctl);
+    if (SH) __threadfence_system(); // the remote halo stores of this CTA are visible before its ticket
     if (threadIdx.x == 0) {
         double *sp = a.spart + (size_t)blockIdx.x * 5;
 #pragma unroll
         for (int q = 0; q < 5; ++q) sp[q] = s[q];
         __threadfence();
         const unsigned t = atomicAdd(&a.ctl->ticket_step, 1u);
-        is_last = (t == gridDim.x - 1);
+        is_last = (t == (unsigned)nact - 1);
     }
     __syncthreads();
     if (!is_last) return;
@@ -620,7 +693,7 @@ __global__ void __launch_bounds__(NL_BS) nl_step_kernel(NlArgs a)
 
     // fixed-order reduction of all CTA partials
     double r[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int b = threadIdx.x; b < a.nblk; b += NL_BS) {
+    for (int b = threadIdx.x; b < (SH ? nact : a.nblk); b += NL_BS) {
 #pragma unroll
         for (int q = 0; q < 5; ++q) r[q] += __ldcg(a.spart + (size_t)b * 5 + q);
     }
@@ -645,7 +718,18 @@ __global__ void __launch_bounds__(NL_BS) nl_step_kernel(NlArgs a)
             a.ctl->cur = 1 - cur;
             a.ctl->unwrapped = 0; // every position the next step reads has been wrapped
             const double m = __longlong_as_double((long long)a.ctl->maxd2_bits);
-            if (m > a.half_skin2) a.ctl->need_rebuild = 1;
+            if (!SH) {
+                if (m > a.half_skin2) a.ctl->need_rebuild = 1;
+            } else {
+                // publish "step seq+1 done (+ skin violated)" to every rank, this one included
+                const int val = ((seq + 1) << 1) | (m > a.half_skin2 ? 1 : 0);
+                const int slot = ((seq + 1) & 1) * LJMD_MAX_RANKS + a.rank;
+                __threadfence_system();
+                for (int q = 0; q < a.world; ++q) nl_st_release_sys(a.peer_flags[q] + slot, val);
+                a.ctl->seq = seq + 1;
+                a.ctl->steps_left -= 1;
+                a.ctl->steps_done += 1;
+            }
         }
         a.ctl->ticket_step = 0;
     }
@@ -740,6 +824,37 @@ __global__ void __launch_bounds__(NL_BS) nl_count_kernel(NlArgs a)
     if ((threadIdx.x & 31) == 0 && a.pair_counts) { atomicAdd(&a.pair_counts[0], ncand); atomicAdd(&a.pair_counts[1], ncut); }
 }
 
+// After a halt: forget the violation bits of the flags already received (both parity slots).
+__global__ void nl_clear_viol_kernel(int *flags)
+{
+    const int t = threadIdx.x;
+    if (t < 2 * LJMD_MAX_RANKS) flags[t] &= ~1;
+}
+
+// Slab sharding: owned slot ranges of the state arrays <-> a dense [narr][cmax] exchange buffer.
+__global__ void __launch_bounds__(256) nl_pack_kernel(NlArgs a, double *buf, int cmax)
+{
+    const int layer = a.nc * a.nc;
+    const int sb = a.cell_start[a.xlo * layer], cnt = a.cell_start[a.xhi * layer] - sb;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    for (int q = 0; q < a.narr; ++q) buf[(size_t)q * cmax + t] = a.arr[q][sb + t];
+}
+
+// recv = [world][narr][cmax]; bounds[q] = first cell layer of rank q (bounds[world] = nc)
+struct NlBounds { int x[LJMD_MAX_RANKS + 1]; };
+__global__ void __launch_bounds__(256) nl_unpack_kernel(NlArgs a, const double *recv, int cmax, NlBounds bd)
+{
+    const int q = blockIdx.y;
+    if (q == a.rank) return; // own range is already in place
+    const int layer = a.nc * a.nc;
+    const int sb = a.cell_start[bd.x[q] * layer], cnt = a.cell_start[bd.x[q + 1] * layer] - sb;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    const double *src = recv + (size_t)q * a.narr * cmax;
+    for (int k = 0; k < a.narr; ++k) a.arr[k][sb + t] = src[(size_t)k * cmax + t];
+}
+
 // ==========================================================================================
 // Host side
 // ==========================================================================================
@@ -792,6 +907,10 @@ static NlArgs make_args(ljmd_ctx *c, int eval_sel)
     a.obs = c->fw.obs;
     a.eval_sel = eval_sel;
     a.pair_counts = nullptr;
+    a.sh_on = w.sh_on; a.rank = w.rank; a.world = w.world; a.xlo = w.xlo; a.xhi = w.xhi;
+    for (int q = 0; q < LJMD_MAX_RANKS; ++q) { a.peer_p4[q] = w.peer_p4[q]; a.peer_flags[q] = w.peer_flags[q]; }
+    a.flags = w.flags;
+    if (w.sh_on) { a.sc.tail_u = 0.0; a.sc.tail_du = 0.0; a.sc.tail_ddu = 0.0; } // added once, after the cross-rank reduction
     return a;
 }
 
@@ -851,6 +970,8 @@ int nlist_plan(ljmd_ctx *c)
     LJMD_CUDA_CHECK(cudaMalloc(&w.alt, sizeof(double) * 15 * (size_t)n));
     LJMD_CUDA_CHECK(cudaMalloc(&w.spart, sizeof(double) * 5 * (size_t)w.nblk));
     LJMD_CUDA_CHECK(cudaMalloc(&w.ctl, sizeof(NlCtl)));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.flags, sizeof(int) * 2 * LJMD_MAX_RANKS));
+    LJMD_CUDA_CHECK(cudaMemsetAsync(w.flags, 0, sizeof(int) * 2 * LJMD_MAX_RANKS, c->stream));
     LJMD_CUDA_CHECK(cudaStreamCreateWithFlags(&w.side_stream, cudaStreamNonBlocking));
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (size_t)w.ncells, c->stream));
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.cell_cursor, 0, sizeof(int) * (size_t)w.ncells, c->stream));
@@ -871,6 +992,11 @@ void nlist_free(ljmd_ctx *c)
     cudaFree(w.cell_of_slot); cudaFree(w.cell_count); cudaFree(w.cell_start); cudaFree(w.cell_cursor); cudaFree(w.tile_sum);
     cudaFree(w.keys); cudaFree(w.orig); cudaFree(w.orig_alt); cudaFree(w.slot_of_orig); cudaFree(w.interior);
     cudaFree(w.nb_cnt); cudaFree(w.nbr); cudaFree(w.p4); cudaFree(w.r0); cudaFree(w.alt); cudaFree(w.spart); cudaFree(w.ctl);
+    for (int q = 0; q < LJMD_MAX_RANKS; ++q) {
+        if (w.ipc_p4[q]) cudaIpcCloseMemHandle(w.ipc_p4[q]);
+        if (w.ipc_flags[q]) cudaIpcCloseMemHandle(w.ipc_flags[q]);
+    }
+    cudaFree(w.flags);
     if (w.side_stream) cudaStreamDestroy(w.side_stream);
 }
 
@@ -917,7 +1043,7 @@ int nlist_enqueue_forces(ljmd_ctx *c)
 {
     LJMD_TRY(nlist_enqueue_rebuild(c, 0));
     const NlArgs a = make_args(c, 0);
-    nl_step_kernel<0, false><<<c->nw.nblk, NL_BS, 0, c->stream>>>(a);
+    nl_step_kernel<0, false, false><<<c->nw.nblk, NL_BS, 0, c->stream>>>(a);
     if (!c->capturing) c->launches++;
     LJMD_CUDA_CHECK(cudaGetLastError());
     return LJMD_OK;
@@ -935,8 +1061,12 @@ int nlist_enqueue_drift(ljmd_ctx *c)
 int nlist_enqueue_step_kernel(ljmd_ctx *c)
 {
     const NlArgs a = make_args(c, 1);
-    if (c->st.rux) nl_step_kernel<1, true><<<c->nw.nblk, NL_BS, 0, c->stream>>>(a);
-    else nl_step_kernel<1, false><<<c->nw.nblk, NL_BS, 0, c->stream>>>(a);
+    if (c->nw.sh_on) {
+        const int grid = c->nw.own_blocks;
+        if (c->st.rux) nl_step_kernel<1, true, true><<<grid, NL_BS, 0, c->stream>>>(a);
+        else nl_step_kernel<1, false, true><<<grid, NL_BS, 0, c->stream>>>(a);
+    } else if (c->st.rux) nl_step_kernel<1, true, false><<<c->nw.nblk, NL_BS, 0, c->stream>>>(a);
+    else nl_step_kernel<1, false, false><<<c->nw.nblk, NL_BS, 0, c->stream>>>(a);
     if (!c->capturing) c->launches++;
     LJMD_CUDA_CHECK(cudaGetLastError());
     c->nw.cur_host ^= 1;
@@ -1064,6 +1194,8 @@ int nlist_check_overflow(ljmd_ctx *c)
     LJMD_CUDA_CHECK(cudaMemcpyAsync(&h, c->nw.ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     c->nw.rebuilds_host = h.rebuilds;
+    if (h.overflow >= 0x40000000)
+        return set_error(LJMD_ERR_UNSUPPORTED, "slab sharding: a rank owns more atoms than its launch capacity (density too inhomogeneous)");
     if (h.overflow > 0)
         return set_error(LJMD_ERR_UNSUPPORTED,
                          "neighbour list capacity exceeded: an atom has %d neighbours within rc+skin, capacity %d "
@@ -1101,9 +1233,249 @@ int nlist_download_cells(ljmd_ctx *c, int32_t *cell_of_atom, int32_t *cell_start
     return LJMD_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Slab sharding of one large system over the GPUs of a node (one process per GPU).
+// ------------------------------------------------------------------------------------------
+static void slab_layers(int nc, int rank, int world, int *xlo, int *xhi)
+{
+    *xlo = (int)((long long)rank * nc / world);
+    *xhi = (int)((long long)(rank + 1) * nc / world);
+}
+
+int nlist_slab_bounds_host(ljmd_ctx *c, int32_t *bounds)
+{
+    const NlistWork &w = c->nw;
+    const int layer = w.nc * w.nc;
+    for (int q = 0; q <= w.world; ++q) {
+        int xlo, xhi;
+        slab_layers(w.nc, q < w.world ? q : 0, w.world, &xlo, &xhi);
+        const int cell = (q < w.world) ? xlo * layer : w.ncells;
+        LJMD_CUDA_CHECK(cudaMemcpyAsync(&bounds[q], w.cell_start + cell, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    }
+    LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return LJMD_OK;
+}
+
 } // namespace ljmd
 
 using namespace ljmd;
+
+extern "C" int ljmd_ctx_slab_export(ljmd_ctx *c, void *handles128, uint64_t *raw_ptrs2)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_slab_export(): ctx is NULL.");
+    if (c->method != LJMD_METHOD_NLIST) return set_error(LJMD_ERR_UNSUPPORTED, "ljmd_ctx_slab_export(): needs the neighbour-list method.");
+    int prev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
+    cudaError_t e = cudaSuccess;
+    if (handles128) {
+        cudaIpcMemHandle_t h[2];
+        e = cudaIpcGetMemHandle(&h[0], c->nw.p4);
+        if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h[1], c->nw.flags);
+        if (e == cudaSuccess) memcpy(handles128, h, sizeof(h));
+    }
+    if (raw_ptrs2) { raw_ptrs2[0] = (uint64_t)(uintptr_t)c->nw.p4; raw_ptrs2[1] = (uint64_t)(uintptr_t)c->nw.flags; }
+    if (prev != c->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return set_error(LJMD_ERR_CUDA, "ljmd_ctx_slab_export(): %s", cudaGetErrorString(e));
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_ctx_slab_attach(ljmd_ctx *c, int32_t rank, int32_t world, const void *all_handles,
+                                    const uint64_t *all_raw_ptrs)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_slab_attach(): ctx is NULL.");
+    if (c->method != LJMD_METHOD_NLIST) return set_error(LJMD_ERR_UNSUPPORTED, "ljmd_ctx_slab_attach(): needs the neighbour-list method.");
+    if (world < 1 || world > LJMD_MAX_RANKS || rank < 0 || rank >= world)
+        return set_error(LJMD_ERR_ARG, "ljmd_ctx_slab_attach(): bad rank %d / world %d (max %d).", rank, world, LJMD_MAX_RANKS);
+    NlistWork &w = c->nw;
+    if (w.nc < world) return set_error(LJMD_ERR_UNSUPPORTED, "ljmd_ctx_slab_attach(): %d cell layers cannot be split over %d ranks.", w.nc, world);
+    if (!all_handles && !all_raw_ptrs) return set_error(LJMD_ERR_NULL, "ljmd_ctx_slab_attach(): no peer handles.");
+    int prev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
+    int rc = LJMD_OK;
+    for (int q = 0; q < world && rc == LJMD_OK; ++q) {
+        if (q == rank) { w.peer_p4[q] = w.p4; w.peer_flags[q] = w.flags; continue; }
+        if (all_raw_ptrs) { // same process (tests): the peers' device pointers are directly usable
+            w.peer_p4[q] = reinterpret_cast<double4 *>((uintptr_t)all_raw_ptrs[2 * q]);
+            w.peer_flags[q] = reinterpret_cast<int *>((uintptr_t)all_raw_ptrs[2 * q + 1]);
+        } else {
+            const cudaIpcMemHandle_t *h = reinterpret_cast<const cudaIpcMemHandle_t *>(all_handles) + 2 * q;
+            void *p = nullptr, *f = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, h[0], cudaIpcMemLazyEnablePeerAccess);
+            if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&f, h[1], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { rc = set_error(LJMD_ERR_CUDA, "ljmd_ctx_slab_attach(): cudaIpcOpenMemHandle(rank %d): %s", q, cudaGetErrorString(e)); break; }
+            w.ipc_p4[q] = p; w.ipc_flags[q] = f;
+            w.peer_p4[q] = reinterpret_cast<double4 *>(p);
+            w.peer_flags[q] = reinterpret_cast<int *>(f);
+        }
+    }
+    if (rc == LJMD_OK) {
+        w.sh_on = 1; w.rank = rank; w.world = world;
+        slab_layers(w.nc, rank, world, &w.xlo, &w.xhi);
+        // CTAs of the step kernel: room for 30 % more atoms than the mean slab (+ one layer's worth)
+        const double mean = (double)c->sc.n * (w.xhi - w.xlo) / w.nc;
+        w.own_blocks = (int)((1.3 * mean + 4096.0) / NL_BS) + 1;
+        if (w.own_blocks > w.nblk) w.own_blocks = w.nblk;
+        if (c->graph_chunk) { cudaGraphExecDestroy(c->graph_chunk); c->graph_chunk = nullptr; }
+        int zero4[4] = {0, 0, 0, 0}; // halted, steps_left, steps_done, seq
+        cudaError_t e = cudaMemcpyAsync(reinterpret_cast<char *>(w.ctl) + offsetof(NlCtl, halted), zero4, sizeof(zero4),
+                                        cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(w.flags, 0, sizeof(int) * 2 * LJMD_MAX_RANKS, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = set_error(LJMD_ERR_CUDA, "ljmd_ctx_slab_attach(): %s", cudaGetErrorString(e));
+    }
+    if (prev != c->device) cudaSetDevice(prev);
+    return rc;
+}
+
+// First slot of every rank's slab (bounds[world] = n), from the current cell table.
+extern "C" int ljmd_ctx_slab_bounds(ljmd_ctx *c, int32_t *bounds)
+{
+    clear_error();
+    if (!c || !bounds) return set_error(LJMD_ERR_NULL, "ljmd_ctx_slab_bounds(): NULL argument.");
+    if (!c->nw.sh_on) return set_error(LJMD_ERR_ARG, "ljmd_ctx_slab_bounds(): context is not sharded.");
+    int prev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
+    const int rc = nlist_slab_bounds_host(c, bounds);
+    if (prev != c->device) cudaSetDevice(prev);
+    return rc;
+}
+
+// Owned slot range of every permuted state array -> dense device buffer [narr][cmax].
+extern "C" int ljmd_ctx_slab_pack(ljmd_ctx *c, double *dev_buf, int32_t cmax, int32_t *narr)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_slab_pack(): ctx is NULL.");
+    if (!c->nw.sh_on) return set_error(LJMD_ERR_ARG, "ljmd_ctx_slab_pack(): context is not sharded.");
+    if (narr) *narr = c->nw.narr;
+    if (!dev_buf) return LJMD_OK; // query only
+    int prev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
+    const NlArgs a = make_args(c, 0);
+    nl_pack_kernel<<<(cmax + 255) / 256, 256, 0, c->stream>>>(a, dev_buf, cmax);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (prev != c->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return set_error(LJMD_ERR_CUDA, "ljmd_ctx_slab_pack(): %s", cudaGetErrorString(e));
+    return LJMD_OK;
+}
+
+// All ranks' packed ranges ([world][narr][cmax]) -> the state arrays (every rank then holds the
+// complete state).
+extern "C" int ljmd_ctx_slab_unpack(ljmd_ctx *c, const double *dev_buf, int32_t cmax)
+{
+    clear_error();
+    if (!c || !dev_buf) return set_error(LJMD_ERR_NULL, "ljmd_ctx_slab_unpack(): NULL argument.");
+    if (!c->nw.sh_on) return set_error(LJMD_ERR_ARG, "ljmd_ctx_slab_unpack(): context is not sharded.");
+    int prev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
+    const NlArgs a = make_args(c, 0);
+    NlBounds bd;
+    for (int q = 0; q <= c->nw.world; ++q) {
+        int xlo, xhi;
+        slab_layers(c->nw.nc, q < c->nw.world ? q : 0, c->nw.world, &xlo, &xhi);
+        bd.x[q] = (q < c->nw.world) ? xlo : c->nw.nc;
+    }
+    dim3 grid((cmax + 255) / 256, c->nw.world);
+    nl_unpack_kernel<<<grid, 256, 0, c->stream>>>(a, dev_buf, cmax, bd);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (prev != c->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return set_error(LJMD_ERR_CUDA, "ljmd_ctx_slab_unpack(): %s", cudaGetErrorString(e));
+    return LJMD_OK;
+}
+
+// Global re-sort + list rebuild for the positions of the NEXT step if the device flag asks for it
+// (a halt sets it) or `force` is non-zero; clears the halt.  Every rank must hold the complete
+// state: call after ljmd_ctx_slab_unpack.
+extern "C" int ljmd_ctx_slab_rebuild(ljmd_ctx *c, int32_t force)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_slab_rebuild(): ctx is NULL.");
+    if (!c->nw.sh_on) return set_error(LJMD_ERR_ARG, "ljmd_ctx_slab_rebuild(): context is not sharded.");
+    int prev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
+    nl_clear_viol_kernel<<<1, 32, 0, c->stream>>>(c->nw.flags);
+    int rc = force ? nlist_request_rebuild(c) : LJMD_OK;
+    const int zero = 0;
+    if (rc == LJMD_OK) {
+        cudaError_t e = cudaMemcpyAsync(reinterpret_cast<char *>(c->nw.ctl) + offsetof(NlCtl, halted), &zero, sizeof(int),
+                                        cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = set_error(LJMD_ERR_CUDA, "ljmd_ctx_slab_rebuild(): %s", cudaGetErrorString(e));
+    }
+    if (rc == LJMD_OK) rc = nlist_enqueue_rebuild(c, 1);
+    if (rc == LJMD_OK) rc = nlist_check_overflow(c);
+    if (prev != c->device) cudaSetDevice(prev);
+    return rc;
+}
+
+// r(t+dt) of ALL atoms from the complete state (start of a sharded run), verlet.f90:58-63.
+extern "C" int ljmd_ctx_slab_drift(ljmd_ctx *c)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_slab_drift(): ctx is NULL.");
+    if (c->method != LJMD_METHOD_NLIST) return set_error(LJMD_ERR_UNSUPPORTED, "ljmd_ctx_slab_drift(): needs the neighbour-list method.");
+    int prev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
+    const int rc = nlist_enqueue_drift(c);
+    if (prev != c->device) cudaSetDevice(prev);
+    return rc;
+}
+
+// Up to max_steps sharded velocity-Verlet steps (the step kernels are launched back to back; once
+// some rank reports a skin violation the remaining ones are no-ops on every rank).  Returns the
+// number of steps actually done and whether the run halted (=> gather + ljmd_ctx_slab_rebuild).
+// obs4 (may be NULL) = this rank's share of {epot, ekin, d_epot, dd_epot} of the last step done,
+// without tail corrections.
+extern "C" int ljmd_ctx_slab_run(ljmd_ctx *c, int32_t max_steps, int32_t *steps_done, int32_t *halted, double *obs4)
+{
+    clear_error();
+    if (!c || !steps_done || !halted) return set_error(LJMD_ERR_NULL, "ljmd_ctx_slab_run(): NULL argument.");
+    if (!c->nw.sh_on) return set_error(LJMD_ERR_ARG, "ljmd_ctx_slab_run(): context is not sharded.");
+    if (max_steps < 0) return set_error(LJMD_ERR_ARG, "ljmd_ctx_slab_run(): max_steps must be >= 0.");
+    int prev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
+    NlistWork &w = c->nw;
+    int rc = LJMD_OK;
+    int *stage = reinterpret_cast<int *>(reinterpret_cast<char *>(c->h_obs) + sizeof(double) * 4 * (size_t)c->R);
+    stage[0] = max_steps; stage[1] = 0; // steps_left, steps_done
+    cudaError_t e = cudaMemcpyAsync(reinterpret_cast<char *>(w.ctl) + offsetof(NlCtl, steps_left), stage, 2 * sizeof(int),
+                                    cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_s0, c->stream);
+    for (int s = 0; s < max_steps && e == cudaSuccess && rc == LJMD_OK; ++s) rc = nlist_enqueue_step_kernel(c);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_s1, c->stream);
+    NlCtl h;
+    memset(&h, 0, sizeof(h));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, w.ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_obs, c->fw.obs, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev_s0, c->ev_s1);
+        c->last_step_ms = ms;
+    }
+    if (prev != c->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return set_error(LJMD_ERR_CUDA, "ljmd_ctx_slab_run(): %s", cudaGetErrorString(e));
+    if (rc != LJMD_OK) return rc;
+    // the host mirror of cur follows the steps that really ran
+    if (((max_steps - h.steps_done) & 1) != 0) w.cur_host ^= 1;
+    *steps_done = h.steps_done;
+    *halted = h.halted;
+    if (h.overflow > 0) return nlist_check_overflow(c);
+    if (obs4) for (int k = 0; k < 4; ++k) obs4[k] = c->h_obs[k];
+    return LJMD_OK;
+}
+
 
 extern "C" int ljmd_ctx_nlist_info(ljmd_ctx *c, double *skin, int32_t *cells_per_edge, int32_t *capacity,
                                    int64_t *rebuilds, int64_t *entries)

@@ -132,6 +132,11 @@ struct NlCtl {
     unsigned pad_;
     unsigned long long maxd2_bits; // max squared displacement since the last build (double bits)
     long long rebuilds;    // number of list builds so far
+    // ---- slab sharding (lj_nlist.cu)
+    int halted;            // a rank reported a skin violation: step kernels are no-ops until the host rebuilds
+    int steps_left;        // step kernels still allowed to run in the current ljmd_ctx_slab_run call
+    int steps_done;        // steps completed in the current ljmd_ctx_slab_run call
+    int seq;               // sharded steps completed since ljmd_ctx_slab_attach
 };
 
 // Neighbour-list work buffers (lj_nlist.cu).  The resident state is kept in cell-sorted order.
@@ -156,6 +161,12 @@ struct NlistWork {
     double4 *p4;         // [2][n] packed positions (x, y, z, 0) of the two position buffers
     NlCtl *ctl;
     cudaStream_t side_stream; // captures the IF-node bodies of the step graph
+    // slab sharding over the GPUs of a node
+    int sh_on, rank, world, xlo, xhi, own_blocks;
+    double4 *peer_p4[LJMD_MAX_RANKS];
+    int *peer_flags[LJMD_MAX_RANKS];
+    void *ipc_p4[LJMD_MAX_RANKS], *ipc_flags[LJMD_MAX_RANKS];
+    int *flags;
 };
 
 } // namespace ljmd

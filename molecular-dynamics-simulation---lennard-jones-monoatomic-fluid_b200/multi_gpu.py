@@ -83,6 +83,84 @@ def ensemble_reduce(sums: np.ndarray, sumsq: np.ndarray, count: int, group=None)
     return mean, np.sqrt(var), int(round(ntot))
 
 
+def slab_layers(nc: int, rank: int, world: int) -> Tuple[int, int]:
+    """Cell layers cx in [lo, hi) owned by `rank` (same rule as the library)."""
+    return rank * nc // world, (rank + 1) * nc // world
+
+
+class SlabRunner:
+    """Drives one rank of a slab-sharded neighbour-list run (include/ljmd.h, ljmd_ctx_slab_*).
+
+    Per step nothing goes through the host or NCCL: the step kernels push their boundary layers
+    into the neighbours' position buffers over NVLink and synchronise through per-step flags.
+    torch.distributed is used (i) once, to exchange the CUDA IPC handles, and (ii) whenever a rank
+    reports a skin violation: one all-gather of the packed slabs, after which every rank re-sorts
+    globally and rebuilds the lists of its own slab.
+
+    `ctx` must hold the COMPLETE state (uploaded on every rank) with forces computed
+    (ctx.compute_forces()).  Reference semantics of a step: physics/verlet.f90:41-97.
+    """
+
+    def __init__(self, ctx, rank: int, world: int, group=None, chunk: int = 32):
+        import torch
+        import torch.distributed as dist
+
+        self.ctx, self.rank, self.world, self.group, self.chunk = ctx, rank, world, group, chunk
+        self.torch, self.dist = torch, dist
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        blob, _ = ctx.slab_export()
+        blobs = [None] * world
+        dist.all_gather_object(blobs, blob, group=group)
+        ctx.slab_attach(rank, world, handles=blobs)
+        self.narr = ctx.slab_narr()
+        self.n = ctx.params.n
+        self.send = self.recv = None
+        self.rebuilds = 0
+        self.steps = 0
+        ctx.slab_drift()     # r(t+dt) of every atom
+        ctx.slab_rebuild()   # only if the drift already violated the skin of the t=0 list
+        self.bounds = ctx.slab_bounds()
+        dist.barrier(group=group)  # every rank is attached before anybody writes into a peer
+
+    def _buffers(self, cmax: int):
+        torch = self.torch
+        if self.send is None or self.send.numel() < self.narr * cmax:
+            cap = int(cmax * 1.2) + 1024
+            self.send = torch.empty(self.narr * cap, dtype=torch.float64, device=self.dev)
+            self.recv = torch.empty(self.world * self.narr * cap, dtype=torch.float64, device=self.dev)
+        return self.send[: self.narr * cmax], self.recv[: self.world * self.narr * cmax]
+
+    def gather(self) -> None:
+        """Complete state on every rank: pack own slab, one all-gather, unpack."""
+        cmax = int(np.max(np.diff(self.bounds)))
+        send, recv = self._buffers(cmax)
+        self.ctx.slab_pack(send.data_ptr(), cmax)
+        self.dist.all_gather_into_tensor(recv, send, group=self.group)
+        self.ctx.slab_unpack(recv.data_ptr(), cmax)
+
+    def step(self, nsteps: int) -> np.ndarray:
+        """nsteps velocity-Verlet steps; returns this rank's observable share of the last step."""
+        left = nsteps
+        obs = np.zeros(4)
+        while left > 0:
+            done, halted, obs = self.ctx.slab_run(min(self.chunk, left))
+            left -= done
+            self.steps += done
+            if halted:
+                self.gather()
+                self.ctx.slab_rebuild()
+                self.rebuilds += 1
+                self.bounds = self.ctx.slab_bounds()
+            elif done == 0 and left > 0:
+                raise RuntimeError("slab run made no progress")
+        return obs
+
+    def finish(self) -> None:
+        """Leave the complete, current state on every rank (for download)."""
+        self.gather()
+
+
 class DeviceArray:
     """Wraps a raw device address so that torch.as_tensor(...) views it without a copy."""
 

@@ -245,3 +245,76 @@ def test_nlist_needs_three_cells(lj):
     with pytest.raises(lj.LjmdError) as ei:
         lj.Context(p, method=lj.METHOD_NLIST)
     assert ei.value.code == 10
+
+
+def test_nlist_slab_two_ranks_emulated(lj, O):
+    """Slab sharding with two 'ranks' emulated as two contexts on one GPU (peer pointers are the
+    other context's device pointers; the all-gather is done by hand with device copies).  One step
+    per launch, alternating, so no kernel ever has to wait for a concurrently running peer.
+    The trajectory must be BITWISE equal to the single-context neighbour-list run."""
+    import importlib
+
+    import torch
+    mg = importlib.import_module(lj.__name__ + ".multi_gpu")
+    p_o, st = make_config(O, "cfg3")
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    nsteps, world = 60, 2
+    dev = torch.device("cuda", 0)
+    with _env(LJMD_NL_SKIN=0.12):
+        with lj.Context(p, method=lj.METHOD_NLIST) as ref:
+            ref.upload(_state(lj, st))
+            ref.compute_forces()
+            ref_obs = ref.step(nsteps)
+            ref_state = ref.download()
+            ref_rebuilds = ref.nlist_info()["rebuilds"]
+        ctxs = [lj.Context(p, method=lj.METHOD_NLIST) for _ in range(world)]
+        try:
+            for c in ctxs:
+                c.upload(_state(lj, st))
+                c.compute_forces()
+            raw = [c.slab_export()[1] for c in ctxs]
+            for r, c in enumerate(ctxs):
+                c.slab_attach(r, world, raw_ptrs=raw)
+                c.slab_drift()
+                c.slab_rebuild()
+            narr = ctxs[0].slab_narr()
+
+            def gather():
+                bounds = ctxs[0].slab_bounds()
+                assert all(np.array_equal(c.slab_bounds(), bounds) for c in ctxs)
+                cmax = int(np.max(np.diff(bounds)))
+                recv = torch.zeros(world * narr * cmax, dtype=torch.float64, device=dev)
+                for r, c in enumerate(ctxs):
+                    c.slab_pack(recv[r * narr * cmax:].data_ptr(), cmax)
+                torch.cuda.synchronize()
+                for c in ctxs:
+                    c.slab_unpack(recv.data_ptr(), cmax)
+                torch.cuda.synchronize()
+
+            done_total, rebuilds, obs = 0, 1, None
+            while done_total < nsteps:
+                res = []
+                for c in ctxs:
+                    res.append(c.slab_run(1))
+                    torch.cuda.synchronize()
+                assert res[0][0] == res[1][0] and res[0][1] == res[1][1]
+                if res[0][0] == 1:
+                    done_total += 1
+                    obs = res[0][2] + res[1][2]
+                if res[0][1]:
+                    gather()
+                    for c in ctxs:
+                        c.slab_rebuild()
+                    rebuilds += 1
+            gather()
+            tails = lj.tail_corrections(p)
+            obs[0] += tails[0]; obs[2] += tails[1]; obs[3] += tails[2]
+            assert rebuilds >= 2  # the initial build + at least one rebuild after a halt
+            assert np.all(np.abs(obs - ref_obs) <= 1e-13 * np.abs(ref_obs))
+            for c in ctxs:
+                d = c.download()
+                for x, y in zip(d.arrays(), ref_state.arrays()):
+                    assert np.array_equal(x, y)
+        finally:
+            for c in ctxs:
+                c.close()
