@@ -204,9 +204,9 @@ def run_slabs(args, w, lj, mg, dist, rank, world, local, n, arrs, p):
     l0, r0 = ctx.launch_count, runner.rebuilds
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    e0.record()
+    e0.record(runner.stream)
     share = runner.step(args.steps)
-    e1.record()
+    e1.record(runner.stream)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     launches = ctx.launch_count - l0
@@ -235,6 +235,9 @@ def run_slabs(args, w, lj, mg, dist, rank, world, local, n, arrs, p):
             "roofline": None, "cpu_baseline": None, "e2e": None, "clocks": clocks,
             "gpu_launches": int(launches * world), "wall_s": wall,
             "obs_last": [float(x) for x in obs],
+            "rank0_profile_ms": {"step_kernels_device": runner.t_run_dev_ms, "slab_run_wall": 1e3 * runner.t_run,
+                                 "gather_wall": 1e3 * runner.t_gather, "rebuild_wall": 1e3 * runner.t_rebuild,
+                                 "note": "whole run incl. warm-up"},
         }
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -253,7 +256,9 @@ def run_sharded(args, w, lj, dist, rank, world, local, n, arrs, p):
     if w["method"] == "nlist":
         return run_slabs(args, w, lj, mg, dist, rank, world, local, n, arrs, p)
     ctx = lj.Context(p, method=lj.METHOD_CELLS, device=local)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream(device=dev)  # library kernels and NCCL calls on ONE explicit stream
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
     ctx.upload(lj.SimState.from_arrays(arrs))
     ib, ie = mg.shard_range(n, rank, world)
     ctx.set_shard(ib, ie)
@@ -346,7 +351,15 @@ def main():
     if lj.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
 
-    sharded = world > 1 and w["method"] in ("cells", "nlist")
+    sharded = (world > 1 or os.environ.get("LJMD_BENCH_FORCE_SLABS")) and w["method"] in ("cells", "nlist")
+    if sharded and dist is None:  # diagnostic: the sharded code path with a single rank
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist_mod.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local))
+        dist = dist_mod
     n, arrs = synthetic_state(w, seed=0 if sharded else rank)
     p = lj.init_params(n, w["L"], w["dt"], w["rc"], w["k"])
     method = {"cells": lj.METHOD_CELLS, "nlist": lj.METHOD_NLIST}.get(w["method"], lj.METHOD_ALLPAIRS)

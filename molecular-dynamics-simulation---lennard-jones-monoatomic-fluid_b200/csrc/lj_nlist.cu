@@ -573,7 +573,7 @@ __device__ __forceinline__ void nl_st_release_sys(int *p, int v)
 // any rank reported a skin violation the kernel halts (no state change) until the host has
 // re-gathered the state and rebuilt the lists.
 template <int MODE, bool TRACK, bool SH>
-__global__ void __launch_bounds__(NL_BS) nl_step_kernel(NlArgs a)
+__global__ void __launch_bounds__(NL_BS, 1024 / NL_BS) nl_step_kernel(NlArgs a) // <= 64 registers: 32 warps per SM hide the gather latency
 {
     __shared__ double scratch[5 * (NL_BS / 32)];
     __shared__ bool is_last;

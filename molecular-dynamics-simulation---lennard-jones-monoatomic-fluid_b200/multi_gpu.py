@@ -108,7 +108,10 @@ class SlabRunner:
         self.ctx, self.rank, self.world, self.group, self.chunk = ctx, rank, world, group, chunk
         self.torch, self.dist = torch, dist
         self.dev = torch.device("cuda", torch.cuda.current_device())
-        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        # one explicit stream for the library's kernels AND the NCCL calls (torch's default stream
+        # has handle 0, which the library reads as "use the context's own stream")
+        self.stream = torch.cuda.Stream(device=self.dev)
+        ctx.set_stream(self.stream.cuda_stream)
         blob, _ = ctx.slab_export()
         blobs = [None] * world
         dist.all_gather_object(blobs, blob, group=group)
@@ -118,6 +121,7 @@ class SlabRunner:
         self.send = self.recv = None
         self.rebuilds = 0
         self.steps = 0
+        self.t_run_dev_ms = self.t_run = self.t_gather = self.t_rebuild = 0.0  # profile of step()
         ctx.slab_drift()     # r(t+dt) of every atom
         ctx.slab_rebuild()   # only if the drift already violated the skin of the t=0 list
         self.bounds = ctx.slab_bounds()
@@ -135,23 +139,34 @@ class SlabRunner:
         """Complete state on every rank: pack own slab, one all-gather, unpack."""
         cmax = int(np.max(np.diff(self.bounds)))
         send, recv = self._buffers(cmax)
-        self.ctx.slab_pack(send.data_ptr(), cmax)
-        self.dist.all_gather_into_tensor(recv, send, group=self.group)
-        self.ctx.slab_unpack(recv.data_ptr(), cmax)
+        with self.torch.cuda.stream(self.stream):
+            self.ctx.slab_pack(send.data_ptr(), cmax)
+            self.dist.all_gather_into_tensor(recv, send, group=self.group)
+            self.ctx.slab_unpack(recv.data_ptr(), cmax)
 
     def step(self, nsteps: int) -> np.ndarray:
         """nsteps velocity-Verlet steps; returns this rank's observable share of the last step."""
         left = nsteps
         obs = np.zeros(4)
+        import time
         while left > 0:
+            t0 = time.perf_counter()
             done, halted, obs = self.ctx.slab_run(min(self.chunk, left))
+            t1 = time.perf_counter()
+            self.t_run += t1 - t0
+            self.t_run_dev_ms += self.ctx.last_step_ms
             left -= done
             self.steps += done
             if halted:
                 self.gather()
+                self.stream.synchronize()
+                t2 = time.perf_counter()
                 self.ctx.slab_rebuild()
                 self.rebuilds += 1
                 self.bounds = self.ctx.slab_bounds()
+                t3 = time.perf_counter()
+                self.t_gather += t2 - t1
+                self.t_rebuild += t3 - t2
             elif done == 0 and left > 0:
                 raise RuntimeError("slab run made no progress")
         return obs
