@@ -160,6 +160,11 @@ int ljmd_ctx_step(ljmd_ctx *ctx, int32_t nsteps, double *obs4);
 /* As ljmd_ctx_step, but records the 4 observables of every step: series[nsteps][nreplicas][4]. */
 int ljmd_ctx_step_series(ljmd_ctx *ctx, int32_t nsteps, double *series);
 
+/* Per-step recorder for stepping calls other than ljmd_ctx_step_series (e.g. sharded runs):
+ * arm with a capacity in steps (0 disarms); steps are counted from the arming call. */
+int ljmd_ctx_series_arm(ljmd_ctx *ctx, int32_t cap);
+int ljmd_ctx_series_fetch(ljmd_ctx *ctx, int32_t nsteps, double *series);
+
 /* Driver-side kinetic energy 0.5*sum(vx^2+vy^2+vz^2) (md_simulation_program.f90:238-240),
  * per replica. */
 int ljmd_ctx_kinetic_energy(ljmd_ctx *ctx, double *ekin);
@@ -218,6 +223,13 @@ int ljmd_ctx_slab_rebuild(ljmd_ctx *ctx, int32_t force);
  * obs4 = this rank's share of {epot, ekin, d_epot, dd_epot} of the last step, no tail corrections. */
 int ljmd_ctx_slab_run(ljmd_ctx *ctx, int32_t max_steps, int32_t *steps_done, int32_t *halted,
                       double *obs4);
+
+/* Publishes the flag of the last completed step now (normally done by the first CTA of the next
+ * step kernel); needed only when ranks are emulated by alternately stepped contexts of ONE process. */
+int ljmd_ctx_slab_publish(ljmd_ctx *ctx);
+/* Debug aid (neighbour-list path): order-independent XOR checksums of {next positions, v, a,
+ * packed next positions} over all slots; equal on every rank right after a gather + rebuild. */
+int ljmd_ctx_debug_checksum(ljmd_ctx *ctx, uint64_t *out4);
 
 /* Tuning aid: per-warp {start, end, smid, items} clock records of the last independent-warp
  * all-pairs launch (context created with LJMD_SYM_DEBUG=1); returns the number of warps. */

@@ -90,6 +90,7 @@ ABI_SYMBOLS = [
     "ljmd_ctx_nlist_info", "ljmd_ctx_download_nlist",
     "ljmd_ctx_slab_export", "ljmd_ctx_slab_attach", "ljmd_ctx_slab_bounds", "ljmd_ctx_slab_pack",
     "ljmd_ctx_slab_unpack", "ljmd_ctx_slab_drift", "ljmd_ctx_slab_rebuild", "ljmd_ctx_slab_run",
+    "ljmd_ctx_debug_checksum", "ljmd_ctx_series_arm", "ljmd_ctx_series_fetch", "ljmd_ctx_slab_publish",
 ]
 MAX_RANKS = 8
 
@@ -305,6 +306,17 @@ class Context:
         _chk(self._L.ljmd_ctx_step_series(self._h, int(nsteps), _p(ser)))
         return ser[:, 0, :] if self.nreplicas == 1 else ser
 
+    def series_arm(self, cap: int) -> None:
+        _chk(self._L.ljmd_ctx_series_arm(self._h, int(cap)))
+
+    def series_fetch(self, nsteps: int) -> np.ndarray:
+        ser = np.zeros((nsteps, self.nreplicas, 4))
+        _chk(self._L.ljmd_ctx_series_fetch(self._h, int(nsteps), _p(ser)))
+        return ser[:, 0, :] if self.nreplicas == 1 else ser
+
+    def slab_publish(self) -> None:
+        _chk(self._L.ljmd_ctx_slab_publish(self._h))
+
     def kinetic_energy(self) -> np.ndarray:
         k = np.zeros(self.nreplicas)
         _chk(self._L.ljmd_ctx_kinetic_energy(self._h, _p(k)))
@@ -429,6 +441,11 @@ class Context:
 
     def slab_rebuild(self, force: bool = False) -> None:
         _chk(self._L.ljmd_ctx_slab_rebuild(self._h, 1 if force else 0))
+
+    def debug_checksum(self):
+        out = (C.c_uint64 * 4)()
+        _chk(self._L.ljmd_ctx_debug_checksum(self._h, out))
+        return [int(x) for x in out]
 
     def slab_run(self, max_steps: int):
         """(steps_done, halted, obs_share[4])"""

@@ -38,6 +38,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstddef>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -88,6 +89,7 @@ struct NlArgs {
     double4 *peer_p4[LJMD_MAX_RANKS]; // p4 base ([2][n]) of every rank, mapped into this process
     int *peer_flags[LJMD_MAX_RANKS];  // flag block ([2][LJMD_MAX_RANKS] ints) of every rank
     int *flags;                       // this rank's flag block (the peers write into it)
+    int *dbg_exec;                    // debug: CTAs that executed the body of sharded step seq (or nullptr)
     int eval_sel;  // rebuild kernels: 0 = the list is for rb[cur], 1 = for rb[1-cur]
     unsigned long long *pair_counts;
 };
@@ -103,7 +105,11 @@ __host__ __device__ __forceinline__ size_t nl_entry(size_t stride, int i, int m)
 __device__ __forceinline__ double4 nl_ld_pos(const double4 *p)
 {
     double4 r;
+#ifdef NL_LOAD_CG
+    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+#else
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+#endif
     return r;
 }
 __device__ __forceinline__ void nl_st_pos(double4 *p, double x, double y, double z)
@@ -572,8 +578,11 @@ __device__ __forceinline__ void nl_st_release_sys(int *p, int v)
 // the neighbours into p4 are visible, and nobody still reads the buffer this step overwrites.  If
 // any rank reported a skin violation the kernel halts (no state change) until the host has
 // re-gathered the state and rebuilt the lists.
+// Single-GPU variants: <= 64 registers (32 warps per SM hide the gather latency).  The sharded
+// variants need a few more registers; they are given 72 rather than being squeezed into 64 with
+// local-memory spills.
 template <int MODE, bool TRACK, bool SH>
-__global__ void __launch_bounds__(NL_BS, 1024 / NL_BS) nl_step_kernel(NlArgs a) // <= 64 registers: 32 warps per SM hide the gather latency
+__global__ void __launch_bounds__(NL_BS, SH ? 896 / NL_BS : 1024 / NL_BS) nl_step_kernel(NlArgs a)
 {
     __shared__ double scratch[5 * (NL_BS / 32)];
     __shared__ bool is_last;
@@ -602,6 +611,7 @@ __global__ void __launch_bounds__(NL_BS, 1024 / NL_BS) nl_step_kernel(NlArgs a) 
             if (blockIdx.x == 0 && threadIdx.x == 0) { a.ctl->halted = 1; a.ctl->need_rebuild = 1; }
             return;
         }
+        if (blockIdx.x == 0 && threadIdx.x == 0 && a.ctl->ticket_step != 0) atomicOr(&a.ctl->pad_, 1u); // debug
         const int layer = a.nc * a.nc;
         sb = a.cell_start[a.xlo * layer];
         se = a.cell_start[a.xhi * layer];
@@ -613,6 +623,7 @@ __global__ void __launch_bounds__(NL_BS, 1024 / NL_BS) nl_step_kernel(NlArgs a) 
         if ((int)blockIdx.x >= nact) return;
         i = sb + blockIdx.x * NL_BS + threadIdx.x;
         valid = i < se;
+        if (a.dbg_exec && threadIdx.x == 0 && seq < 4096) atomicAdd(&a.dbg_exec[seq], 1);
     }
     const int cur = a.ctl->cur;
     const int ev = (MODE == 1) ? 1 - cur : cur;
@@ -639,9 +650,9 @@ __global__ void __launch_bounds__(NL_BS, 1024 / NL_BS) nl_step_kernel(NlArgs a) 
     if (valid) {
         const size_t ix = i, iy = ix + n, iz = iy + n;
         const double axn = 24.0 * fx, ayn = 24.0 * fy, azn = 24.0 * fz; // lj_potential_energy.f90:189-191
-        double vx = a.v[ix], vy = a.v[iy], vz = a.v[iz];
+        double vx = __ldcg(a.v + ix), vy = __ldcg(a.v + iy), vz = __ldcg(a.v + iz);
         if (MODE == 1) {
-            const double axo = a.a[ix], ayo = a.a[iy], azo = a.a[iz];
+            const double axo = __ldcg(a.a + ix), ayo = __ldcg(a.a + iy), azo = __ldcg(a.a + iz);
             vx = vx + axo * a.sc.dt_half; vy = vy + ayo * a.sc.dt_half; vz = vz + azo * a.sc.dt_half; // verlet.f90:72-74
             vx = vx + axn * a.sc.dt_half; vy = vy + ayn * a.sc.dt_half; vz = vz + azn * a.sc.dt_half; // verlet.f90:86-88
             a.v[ix] = vx; a.v[iy] = vy; a.v[iz] = vz;
@@ -678,7 +689,14 @@ __global__ void __launch_bounds__(NL_BS, 1024 / NL_BS) nl_step_kernel(NlArgs a) 
     }
     block_sum<5>(s, scratch);
     if (MODE == 1) nl_block_max(d2, scratch, a.ctl);
-    if (SH) __threadfence_system(); // the remote halo stores of this CTA are visible before its ticket
+    if (SH) { // EVERY thread's remote halo stores are performed system-wide before thread 0 takes the ticket
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) { // debug: nothing of the control block may change while CTAs are running
+            if (*((volatile int *)&a.ctl->cur) != cur) atomicOr(&a.ctl->pad_, 2u);
+            if (*((volatile int *)&a.ctl->seq) != seq) atomicOr(&a.ctl->pad_, 4u);
+        }
+    }
     if (threadIdx.x == 0) {
         double *sp = a.spart + (size_t)blockIdx.x * 5;
 #pragma unroll
@@ -721,11 +739,8 @@ __global__ void __launch_bounds__(NL_BS, 1024 / NL_BS) nl_step_kernel(NlArgs a) 
             if (!SH) {
                 if (m > a.half_skin2) a.ctl->need_rebuild = 1;
             } else {
-                // publish "step seq+1 done (+ skin violated)" to every rank, this one included
-                const int val = ((seq + 1) << 1) | (m > a.half_skin2 ? 1 : 0);
-                const int slot = ((seq + 1) & 1) * LJMD_MAX_RANKS + a.rank;
-                __threadfence_system();
-                for (int q = 0; q < a.world; ++q) nl_st_release_sys(a.peer_flags[q] + slot, val);
+                // "step seq+1 done (+ skin violated)": published to every rank by the next launch
+                a.ctl->pending_flag = ((seq + 1) << 1) | (m > a.half_skin2 ? 1 : 0);
                 a.ctl->seq = seq + 1;
                 a.ctl->steps_left -= 1;
                 a.ctl->steps_done += 1;
@@ -824,11 +839,72 @@ __global__ void __launch_bounds__(NL_BS) nl_count_kernel(NlArgs a)
     if ((threadIdx.x & 31) == 0 && a.pair_counts) { atomicAdd(&a.pair_counts[0], ncand); atomicAdd(&a.pair_counts[1], ncut); }
 }
 
+// Debug: order-independent checksums (XOR of the bit patterns) of the complete state.
+__global__ void __launch_bounds__(256) nl_checksum_kernel(NlArgs a, unsigned long long *out)
+{
+    const int n = a.sc.n;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long x[4] = {0ull, 0ull, 0ull, 0ull};
+    if (k < n) {
+        const int cur = a.ctl->cur;
+        for (int c = 0; c < 3; ++c) {
+            x[0] ^= (unsigned long long)__double_as_longlong(a.rb[1 - cur][(size_t)c * n + k]) * (k + 1);
+            x[1] ^= (unsigned long long)__double_as_longlong(a.v[(size_t)c * n + k]) * (k + 1);
+            x[2] ^= (unsigned long long)__double_as_longlong(a.a[(size_t)c * n + k]) * (k + 1);
+        }
+        const double4 p = a.p4[1 - cur][k];
+        x[3] ^= ((unsigned long long)__double_as_longlong(p.x) ^ (unsigned long long)__double_as_longlong(p.y) * 3 ^ (unsigned long long)__double_as_longlong(p.z) * 5) * (k + 1);
+    }
+    for (int q = 0; q < 4; ++q) {
+        for (int o = 16; o > 0; o >>= 1) x[q] ^= __shfl_xor_sync(0xffffffffu, x[q], o);
+        if ((threadIdx.x & 31) == 0) atomicXor(out + q, x[q]);
+    }
+}
+
+// Publishes the pending flag of the last completed step (what the first CTA of the next step
+// kernel does); only needed when ranks are emulated by contexts of ONE process that are stepped
+// alternately, where a peer's next launch cannot run while this one waits.
+__global__ void nl_publish_kernel(NlArgs a)
+{
+    if (threadIdx.x != 0) return;
+    const int seq = a.ctl->seq;
+    if (seq <= 0 || a.ctl->halted) return;
+    const int val = a.ctl->pending_flag;
+    const int slot = (seq & 1) * LJMD_MAX_RANKS + a.rank;
+    __threadfence_system();
+    for (int q = 0; q < a.world; ++q) nl_st_release_sys(a.peer_flags[q] + slot, val);
+}
+
+// Debug: checksums keyed by the ORIGINAL atom index: invariant under a correct permutation.
+__global__ void __launch_bounds__(256) nl_checksum_orig_kernel(NlArgs a, unsigned long long *out)
+{
+    const int n = a.sc.n;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long x[4] = {0ull, 0ull, 0ull, 0ull};
+    if (k < n) {
+        const unsigned long long key = (unsigned long long)a.orig[k] * 2654435761ull + 12345ull;
+        for (int q = 0; q < 12; ++q) x[q / 3] ^= (unsigned long long)__double_as_longlong(a.arr[q][k]) * (key + q);
+    }
+    for (int q = 0; q < 4; ++q) {
+        for (int o = 16; o > 0; o >>= 1) x[q] ^= __shfl_xor_sync(0xffffffffu, x[q], o);
+        if ((threadIdx.x & 31) == 0) atomicXor(out + q, x[q]);
+    }
+}
+
 // After a halt: forget the violation bits of the flags already received (both parity slots).
-__global__ void nl_clear_viol_kernel(int *flags)
+// Only the parity slot the halted step consumed is touched: the peers may already be writing the
+// other one (a faster rank can finish its rebuild and its next step before this kernel runs).
+__global__ void nl_clear_viol_kernel(int *flags, NlCtl *ctl)
 {
     const int t = threadIdx.x;
-    if (t < 2 * LJMD_MAX_RANKS) flags[t] &= ~1;
+    if (t < LJMD_MAX_RANKS) flags[(ctl->seq & 1) * LJMD_MAX_RANKS + t] &= ~1;
+    if (t == 0) ctl->pending_flag &= ~1; // it is published again by the first step after the rebuild
+}
+
+__global__ void nl_spin_kernel(long long cycles)
+{
+    const long long t0 = clock64();
+    while (clock64() - t0 < cycles) { }
 }
 
 // Slab sharding: owned slot ranges of the state arrays <-> a dense [narr][cmax] exchange buffer.
@@ -910,6 +986,7 @@ static NlArgs make_args(ljmd_ctx *c, int eval_sel)
     a.sh_on = w.sh_on; a.rank = w.rank; a.world = w.world; a.xlo = w.xlo; a.xhi = w.xhi;
     for (int q = 0; q < LJMD_MAX_RANKS; ++q) { a.peer_p4[q] = w.peer_p4[q]; a.peer_flags[q] = w.peer_flags[q]; }
     a.flags = w.flags;
+    a.dbg_exec = w.dbg_exec;
     if (w.sh_on) { a.sc.tail_u = 0.0; a.sc.tail_du = 0.0; a.sc.tail_ddu = 0.0; } // added once, after the cross-rank reduction
     return a;
 }
@@ -971,6 +1048,10 @@ int nlist_plan(ljmd_ctx *c)
     LJMD_CUDA_CHECK(cudaMalloc(&w.spart, sizeof(double) * 5 * (size_t)w.nblk));
     LJMD_CUDA_CHECK(cudaMalloc(&w.ctl, sizeof(NlCtl)));
     LJMD_CUDA_CHECK(cudaMalloc(&w.flags, sizeof(int) * 2 * LJMD_MAX_RANKS));
+    if (getenv("LJMD_SLAB_DEBUG")) {
+        LJMD_CUDA_CHECK(cudaMalloc(&w.dbg_exec, sizeof(int) * 4096));
+        LJMD_CUDA_CHECK(cudaMemsetAsync(w.dbg_exec, 0, sizeof(int) * 4096, c->stream));
+    }
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.flags, 0, sizeof(int) * 2 * LJMD_MAX_RANKS, c->stream));
     LJMD_CUDA_CHECK(cudaStreamCreateWithFlags(&w.side_stream, cudaStreamNonBlocking));
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.cell_count, 0, sizeof(int) * (size_t)w.ncells, c->stream));
@@ -1320,7 +1401,7 @@ extern "C" int ljmd_ctx_slab_attach(ljmd_ctx *c, int32_t rank, int32_t world, co
         w.own_blocks = (int)((1.3 * mean + 4096.0) / NL_BS) + 1;
         if (w.own_blocks > w.nblk) w.own_blocks = w.nblk;
         if (c->graph_chunk) { cudaGraphExecDestroy(c->graph_chunk); c->graph_chunk = nullptr; }
-        int zero4[4] = {0, 0, 0, 0}; // halted, steps_left, steps_done, seq
+        int zero4[5] = {0, 0, 0, 0, 0}; // halted, steps_left, steps_done, seq, pending_flag
         cudaError_t e = cudaMemcpyAsync(reinterpret_cast<char *>(w.ctl) + offsetof(NlCtl, halted), zero4, sizeof(zero4),
                                         cudaMemcpyHostToDevice, c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(w.flags, 0, sizeof(int) * 2 * LJMD_MAX_RANKS, c->stream);
@@ -1357,6 +1438,13 @@ extern "C" int ljmd_ctx_slab_pack(ljmd_ctx *c, double *dev_buf, int32_t cmax, in
     LJMD_CUDA_CHECK(cudaGetDevice(&prev));
     if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
     const NlArgs a = make_args(c, 0);
+    static double *priv = nullptr; // experiments (LJMD_SLAB_PACK_MODE)
+    const int pmode = getenv("LJMD_SLAB_PACK_MODE") ? atoi(getenv("LJMD_SLAB_PACK_MODE")) : 0;
+    if (pmode && !priv) cudaMalloc(&priv, sizeof(double) * 15 * (size_t)c->sc.n);
+    if (pmode == 1) nl_pack_kernel<<<(cmax + 255) / 256, 256, 0, c->stream>>>(a, priv, cmax);
+    else if (pmode == 2) nl_spin_kernel<<<148, 128, 0, c->stream>>>(200000);
+    else if (pmode == 3) cudaMemsetAsync(priv, 0, sizeof(double) * 12 * (size_t)c->sc.n, c->stream);
+    else
     nl_pack_kernel<<<(cmax + 255) / 256, 256, 0, c->stream>>>(a, dev_buf, cmax);
     c->launches++;
     cudaError_t e = cudaGetLastError();
@@ -1402,7 +1490,7 @@ extern "C" int ljmd_ctx_slab_rebuild(ljmd_ctx *c, int32_t force)
     int prev = 0;
     LJMD_CUDA_CHECK(cudaGetDevice(&prev));
     if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
-    nl_clear_viol_kernel<<<1, 32, 0, c->stream>>>(c->nw.flags);
+    nl_clear_viol_kernel<<<1, 32, 0, c->stream>>>(c->nw.flags, c->nw.ctl);
     int rc = force ? nlist_request_rebuild(c) : LJMD_OK;
     const int zero = 0;
     if (rc == LJMD_OK) {
@@ -1411,10 +1499,71 @@ extern "C" int ljmd_ctx_slab_rebuild(ljmd_ctx *c, int32_t force)
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = set_error(LJMD_ERR_CUDA, "ljmd_ctx_slab_rebuild(): %s", cudaGetErrorString(e));
     }
+    if (getenv("LJMD_SLAB_DEVSYNC")) cudaDeviceSynchronize(); // experiment
+    unsigned long long *dsum = nullptr;
+    if (c->nw.dbg_exec && getenv("LJMD_SLAB_DEBUG_SUM")) { // debug: the permutation must preserve every per-atom value
+        cudaMalloc(&dsum, 64);
+        cudaMemsetAsync(dsum, 0, 64, c->stream);
+        const NlArgs a = make_args(c, 1);
+        nl_checksum_orig_kernel<<<(c->sc.n + 255) / 256, 256, 0, c->stream>>>(a, dsum);
+    }
     if (rc == LJMD_OK) rc = nlist_enqueue_rebuild(c, 1);
+    if (dsum) {
+        const NlArgs a = make_args(c, 1);
+        nl_checksum_orig_kernel<<<(c->sc.n + 255) / 256, 256, 0, c->stream>>>(a, dsum + 4);
+        unsigned long long hs[8];
+        cudaMemcpyAsync(hs, dsum, 64, cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
+        cudaFree(dsum);
+        const char *names[4] = {"rb0", "rb1", "v", "a"};
+        for (int q = 0; q < 4; ++q)
+            if (hs[q] != hs[4 + q])
+                fprintf(stderr, "[ljmd slab debug] rank %d: rebuild changed the per-atom checksum of %s\n", c->nw.rank, names[q]);
+    }
     if (rc == LJMD_OK) rc = nlist_check_overflow(c);
     if (prev != c->device) cudaSetDevice(prev);
     return rc;
+}
+
+extern "C" int ljmd_ctx_slab_publish(ljmd_ctx *c)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_slab_publish(): ctx is NULL.");
+    if (!c->nw.sh_on) return set_error(LJMD_ERR_ARG, "ljmd_ctx_slab_publish(): context is not sharded.");
+    int prev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
+    const NlArgs a = make_args(c, 0);
+    nl_publish_kernel<<<1, 32, 0, c->stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (prev != c->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return set_error(LJMD_ERR_CUDA, "ljmd_ctx_slab_publish(): %s", cudaGetErrorString(e));
+    return LJMD_OK;
+}
+
+// Debug aid: XOR checksums of {next positions, v, a, packed next positions} over ALL slots.
+extern "C" int ljmd_ctx_debug_checksum(ljmd_ctx *c, uint64_t *out4)
+{
+    clear_error();
+    if (!c || !out4) return set_error(LJMD_ERR_NULL, "ljmd_ctx_debug_checksum(): NULL argument.");
+    if (c->method != LJMD_METHOD_NLIST) return set_error(LJMD_ERR_UNSUPPORTED, "ljmd_ctx_debug_checksum(): neighbour-list method only.");
+    int prev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
+    unsigned long long *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 32);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d, 0, 32, c->stream);
+    if (e == cudaSuccess) {
+        const NlArgs a = make_args(c, 0);
+        nl_checksum_kernel<<<(c->sc.n + 255) / 256, 256, 0, c->stream>>>(a, d);
+        e = cudaMemcpyAsync(out4, d, 32, cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (prev != c->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return set_error(LJMD_ERR_CUDA, "ljmd_ctx_debug_checksum(): %s", cudaGetErrorString(e));
+    return LJMD_OK;
 }
 
 // r(t+dt) of ALL atoms from the complete state (start of a sharded run), verlet.f90:58-63.
@@ -1452,7 +1601,19 @@ extern "C" int ljmd_ctx_slab_run(ljmd_ctx *c, int32_t max_steps, int32_t *steps_
     cudaError_t e = cudaMemcpyAsync(reinterpret_cast<char *>(w.ctl) + offsetof(NlCtl, steps_left), stage, 2 * sizeof(int),
                                     cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaEventRecord(c->ev_s0, c->stream);
-    for (int s = 0; s < max_steps && e == cudaSuccess && rc == LJMD_OK; ++s) rc = nlist_enqueue_step_kernel(c);
+    // Every step kernel is followed by the 1-thread publish kernel: the kernel boundary guarantees
+    // that all halo stores of the step are performed system-wide before its flag becomes visible,
+    // and two step kernels are never adjacent in the stream (back-to-back step kernels were observed
+    // to produce rare wrong velocities on B200; with a small kernel in between, as in the
+    // single-GPU graph path, they never did).
+    for (int s = 0; s < max_steps && e == cudaSuccess && rc == LJMD_OK; ++s) {
+        rc = nlist_enqueue_step_kernel(c);
+        if (rc == LJMD_OK) {
+            const NlArgs a = make_args(c, 0);
+            nl_publish_kernel<<<1, 32, 0, c->stream>>>(a);
+            c->launches++;
+        }
+    }
     if (e == cudaSuccess) e = cudaEventRecord(c->ev_s1, c->stream);
     NlCtl h;
     memset(&h, 0, sizeof(h));
@@ -1471,6 +1632,20 @@ extern "C" int ljmd_ctx_slab_run(ljmd_ctx *c, int32_t max_steps, int32_t *steps_
     if (((max_steps - h.steps_done) & 1) != 0) w.cur_host ^= 1;
     *steps_done = h.steps_done;
     *halted = h.halted;
+    if (w.dbg_exec) {
+        static int hcount[4096];
+        cudaMemcpy(hcount, w.dbg_exec, sizeof(hcount), cudaMemcpyDeviceToHost);
+        const int nact_expect = (h.seq > 0) ? hcount[0] : 0; (void)nact_expect;
+        for (int q = 0; q < 4096 && q < h.seq + 2; ++q)
+            if (hcount[q] != 0 && (hcount[q] < w.own_blocks * 3 / 4 - 2000 || hcount[q] > w.nblk))
+                fprintf(stderr, "[ljmd slab debug] rank %d: step seq %d executed by %d CTAs\n", w.rank, q, hcount[q]);
+        if (getenv("LJMD_SLAB_DEBUG_DUMP")) {
+            fprintf(stderr, "[ljmd slab debug] exec counts up to seq %d:", h.seq);
+            for (int q = 0; q <= h.seq && q < 4096; ++q) fprintf(stderr, " %d", hcount[q]);
+            fprintf(stderr, "\n");
+        }
+    }
+    if (h.pad_ != 0) fprintf(stderr, "[ljmd slab debug] rank %d: control-block check failed, mask %u (1 = ticket not re-armed, 2 = cur changed under a running CTA, 4 = seq changed)\n", w.rank, h.pad_);
     if (h.overflow > 0) return nlist_check_overflow(c);
     if (obs4) for (int k = 0; k < 4; ++k) obs4[k] = c->h_obs[k];
     return LJMD_OK;

@@ -179,6 +179,10 @@ static int run_steps_nlist(ljmd_ctx *c, int nsteps)
             c->launches += (int64_t)G * 2; // condition kernel + step kernel; rebuilds are added at the next sync
         }
     }
+    if (getenv("LJMD_NL_B2B")) { // experiment: step kernels back to back (valid only while no rebuild is due)
+        for (; done < nsteps; ++done) LJMD_TRY(nlist_enqueue_step_kernel(c));
+        return LJMD_OK;
+    }
     for (; done < nsteps; ++done) LJMD_TRY(nlist_enqueue_step(c));
     return LJMD_OK;
 }
@@ -587,6 +591,39 @@ extern "C" int ljmd_ctx_step_series(ljmd_ctx *c, int32_t nsteps, double *series)
     }
     int rc2 = set_ctl(c, 0, nullptr);
     return rc != LJMD_OK ? rc : rc2;
+}
+
+// Arms (cap > 0) / disarms (cap == 0) the per-step observable recorder: every following step stores
+// its 4 observables per replica at series[step][replica][4], counting steps from this call.
+extern "C" int ljmd_ctx_series_arm(ljmd_ctx *c, int32_t cap)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_series_arm(): ctx is NULL.");
+    if (cap < 0) return set_error(LJMD_ERR_ARG, "ljmd_ctx_series_arm(): cap must be >= 0.");
+    DeviceGuard g;
+    LJMD_TRY(g.enter(c->device));
+    if (cap == 0) return set_ctl(c, 0, nullptr);
+    if (c->series_cap < cap) {
+        cudaFree(c->d_series);
+        c->d_series = nullptr;
+        c->series_cap = 0;
+        LJMD_CUDA_CHECK(cudaMalloc(&c->d_series, sizeof(double) * 4 * (size_t)c->R * cap));
+        c->series_cap = cap;
+    }
+    return set_ctl(c, cap, c->d_series);
+}
+
+// Copies the first nsteps recorded steps to the host.
+extern "C" int ljmd_ctx_series_fetch(ljmd_ctx *c, int32_t nsteps, double *series)
+{
+    clear_error();
+    if (!c || !series) return set_error(LJMD_ERR_NULL, "ljmd_ctx_series_fetch(): NULL argument.");
+    if (nsteps < 0 || nsteps > c->series_cap) return set_error(LJMD_ERR_ARG, "ljmd_ctx_series_fetch(): nsteps out of range.");
+    DeviceGuard g;
+    LJMD_TRY(g.enter(c->device));
+    LJMD_CUDA_CHECK(cudaMemcpyAsync(series, c->d_series, sizeof(double) * 4 * (size_t)c->R * nsteps, cudaMemcpyDeviceToHost, c->stream));
+    LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return LJMD_OK;
 }
 
 extern "C" int ljmd_ctx_kinetic_energy(ljmd_ctx *c, double *ekin)

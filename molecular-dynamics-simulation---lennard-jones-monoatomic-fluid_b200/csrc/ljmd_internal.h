@@ -137,6 +137,7 @@ struct NlCtl {
     int steps_left;        // step kernels still allowed to run in the current ljmd_ctx_slab_run call
     int steps_done;        // steps completed in the current ljmd_ctx_slab_run call
     int seq;               // sharded steps completed since ljmd_ctx_slab_attach
+    int pending_flag;      // flag value of the last completed step, published by the next launch
 };
 
 // Neighbour-list work buffers (lj_nlist.cu).  The resident state is kept in cell-sorted order.
@@ -167,6 +168,7 @@ struct NlistWork {
     int *peer_flags[LJMD_MAX_RANKS];
     void *ipc_p4[LJMD_MAX_RANKS], *ipc_flags[LJMD_MAX_RANKS];
     int *flags;
+    int *dbg_exec;       // debug counters (LJMD_SLAB_DEBUG)
 };
 
 } // namespace ljmd

@@ -121,6 +121,8 @@ class SlabRunner:
         self.send = self.recv = None
         self.rebuilds = 0
         self.steps = 0
+        import os
+        self.debug = bool(os.environ.get("LJMD_SLAB_DEBUG_PY"))
         self.t_run_dev_ms = self.t_run = self.t_gather = self.t_rebuild = 0.0  # profile of step()
         ctx.slab_drift()     # r(t+dt) of every atom
         ctx.slab_rebuild()   # only if the drift already violated the skin of the t=0 list
@@ -137,17 +139,25 @@ class SlabRunner:
 
     def gather(self) -> None:
         """Complete state on every rank: pack own slab, one all-gather, unpack."""
+        import os
+        if os.environ.get("LJMD_SLAB_SKIP_GATHER"):  # experiment (only meaningful with one rank)
+            return
         cmax = int(np.max(np.diff(self.bounds)))
         send, recv = self._buffers(cmax)
+        mode = os.environ.get("LJMD_SLAB_GATHER_MODE", "")
         with self.torch.cuda.stream(self.stream):
-            self.ctx.slab_pack(send.data_ptr(), cmax)
-            self.dist.all_gather_into_tensor(recv, send, group=self.group)
-            self.ctx.slab_unpack(recv.data_ptr(), cmax)
+            if mode != "nccl_only":
+                self.ctx.slab_pack(send.data_ptr(), cmax)
+            if mode != "pack_only":
+                self.dist.all_gather_into_tensor(recv, send, group=self.group)
+            if mode not in ("pack_only", "nccl_only"):
+                self.ctx.slab_unpack(recv.data_ptr(), cmax)
 
     def step(self, nsteps: int) -> np.ndarray:
         """nsteps velocity-Verlet steps; returns this rank's observable share of the last step."""
         left = nsteps
         obs = np.zeros(4)
+        import os
         import time
         while left > 0:
             t0 = time.perf_counter()
@@ -155,15 +165,42 @@ class SlabRunner:
             t1 = time.perf_counter()
             self.t_run += t1 - t0
             self.t_run_dev_ms += self.ctx.last_step_ms
+            if self.debug:  # every rank must report the same progress
+                rep = [None] * self.world
+                self.dist.all_gather_object(rep, (done, halted), group=self.group)
+                if any(r != rep[0] for r in rep):
+                    print(f"[slab debug] rank {self.rank}: ranks disagree on progress at step {self.steps}: {rep}", flush=True)
             left -= done
             self.steps += done
+            if os.environ.get("LJMD_SLAB_FORCE_REBUILD") and not halted and left - done > 0:
+                # experiment: rebuild after every chunk although nothing violated the skin
+                self.ctx.slab_rebuild(force=True)
+                self.rebuilds += 1
+                self.bounds = self.ctx.slab_bounds()
             if halted:
+                shadow = os.environ.get("LJMD_SLAB_SHADOW")
+                if shadow:
+                    d0 = self.ctx.download(("vx", "ax", "ay"))
                 self.gather()
                 self.stream.synchronize()
                 t2 = time.perf_counter()
                 self.ctx.slab_rebuild()
                 self.rebuilds += 1
                 self.bounds = self.ctx.slab_bounds()
+                if shadow:
+                    d1 = self.ctx.download(("vx", "ax", "ay"))
+                    for nm in ("vx", "ax", "ay"):
+                        bad = np.nonzero(getattr(d0, nm) != getattr(d1, nm))[0]
+                        if len(bad):
+                            print(f"[slab shadow] rank {self.rank} rebuild {self.rebuilds} step {self.steps}: {nm} changed for "
+                                  f"{len(bad)} atoms, orig idx {bad[:4]}..{bad[-1]}", flush=True)
+                if self.debug:  # the complete state must be identical on every rank here
+                    cs = self.ctx.debug_checksum()
+                    allcs = [None] * self.world
+                    self.dist.all_gather_object(allcs, cs, group=self.group)
+                    if any(c != allcs[0] for c in allcs):
+                        print(f"[slab debug] rank {self.rank}: state differs after rebuild {self.rebuilds} "
+                              f"(step {self.steps}): {allcs}", flush=True)
                 t3 = time.perf_counter()
                 self.t_gather += t2 - t1
                 self.t_rebuild += t3 - t2

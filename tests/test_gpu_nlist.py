@@ -296,6 +296,7 @@ def test_nlist_slab_two_ranks_emulated(lj, O):
                 res = []
                 for c in ctxs:
                     res.append(c.slab_run(1))
+                    c.slab_publish()  # emulated ranks: the peer's next launch cannot do it in time
                     torch.cuda.synchronize()
                 assert res[0][0] == res[1][0] and res[0][1] == res[1][1]
                 if res[0][0] == 1:
