@@ -579,10 +579,10 @@ __device__ __forceinline__ void nl_st_release_sys(int *p, int v)
 // any rank reported a skin violation the kernel halts (no state change) until the host has
 // re-gathered the state and rebuilt the lists.
 // Single-GPU variants: <= 64 registers (32 warps per SM hide the gather latency).  The sharded
-// variants need a few more registers; they are given 72 rather than being squeezed into 64 with
+// variants need a few more registers; they get up to 85 rather than being squeezed into 64 with
 // local-memory spills.
 template <int MODE, bool TRACK, bool SH>
-__global__ void __launch_bounds__(NL_BS, SH ? 896 / NL_BS : 1024 / NL_BS) nl_step_kernel(NlArgs a)
+__global__ void __launch_bounds__(NL_BS, (SH || MODE == 0) ? 768 / NL_BS : 1024 / NL_BS) nl_step_kernel(NlArgs a)
 {
     __shared__ double scratch[5 * (NL_BS / 32)];
     __shared__ bool is_last;
@@ -611,7 +611,6 @@ __global__ void __launch_bounds__(NL_BS, SH ? 896 / NL_BS : 1024 / NL_BS) nl_ste
             if (blockIdx.x == 0 && threadIdx.x == 0) { a.ctl->halted = 1; a.ctl->need_rebuild = 1; }
             return;
         }
-        if (blockIdx.x == 0 && threadIdx.x == 0 && a.ctl->ticket_step != 0) atomicOr(&a.ctl->pad_, 1u); // debug
         const int layer = a.nc * a.nc;
         sb = a.cell_start[a.xlo * layer];
         se = a.cell_start[a.xhi * layer];
@@ -692,10 +691,6 @@ __global__ void __launch_bounds__(NL_BS, SH ? 896 / NL_BS : 1024 / NL_BS) nl_ste
     if (SH) { // EVERY thread's remote halo stores are performed system-wide before thread 0 takes the ticket
         __threadfence_system();
         __syncthreads();
-        if (threadIdx.x == 0) { // debug: nothing of the control block may change while CTAs are running
-            if (*((volatile int *)&a.ctl->cur) != cur) atomicOr(&a.ctl->pad_, 2u);
-            if (*((volatile int *)&a.ctl->seq) != seq) atomicOr(&a.ctl->pad_, 4u);
-        }
     }
     if (threadIdx.x == 0) {
         double *sp = a.spart + (size_t)blockIdx.x * 5;
