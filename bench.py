@@ -46,6 +46,7 @@ WORKLOADS = {
     "cfg3_cells": dict(k=20, L=34.19951893353394, rc=2.5, dt=1e-3, method="cells", T=1.0),
     "dense32k": dict(k=20, L=40.0, rc=19.6, dt=1e-4, method="allpairs", T=1.416),  # tuning only
     "cfg4_cells": dict(k=64, L=109.4384605873086, rc=2.5, dt=1e-3, method="cells", T=1.0),
+    "cfg5_ensemble": dict(k=5, L=10.0, rc=4.9, dt=1e-4, method="allpairs", T=1.416, replicas=64),  # per GPU
     "cfg3_nlist": dict(k=20, L=34.19951893353394, rc=2.5, dt=1e-3, method="nlist", T=1.0),
     "cfg4_nlist": dict(k=64, L=109.4384605873086, rc=2.5, dt=1e-3, method="nlist", T=1.0),
 }
@@ -365,7 +366,11 @@ def main():
     method = {"cells": lj.METHOD_CELLS, "nlist": lj.METHOD_NLIST}.get(w["method"], lj.METHOD_ALLPAIRS)
     if sharded:
         return run_sharded(args, w, lj, dist, rank, world, local, n, arrs, p)
-    ctx = lj.Context(p, method=method, device=local)
+    R = int(w.get("replicas", 1))
+    if R > 1:  # ensemble of independent replicas: replica r of rank q gets its own seed
+        reps = [synthetic_state(w, seed=1000 * rank + r)[1] for r in range(R)]
+        arrs = [np.ascontiguousarray(np.stack([reps[r][k] for r in range(R)])) for k in range(9)]
+    ctx = lj.Context(p, method=method, device=local, nreplicas=R)
     ctx.upload(lj.SimState.from_arrays(arrs))
     ctx.compute_forces()
 
@@ -394,7 +399,7 @@ def main():
         t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed = float(t.item())
-    value = n * args.steps * world / elapsed
+    value = n * R * args.steps * world / elapsed
     if not np.all(np.isfinite(obs)):
         raise SystemExit(f"bench.py: non-finite observables {obs}")
 
@@ -424,23 +429,47 @@ def main():
                        "MEASURED_PEAKS.json has no FP64 entry (nominal 37 TFLOP/s)",
         "pair_interactions_per_s": cut / (force_ms * 1e-3),
         "candidate_pairs_per_s": cand / (force_ms * 1e-3),
-        "hbm_note": "state is %.1f KB, L2-resident; HBM is not the bound for all-pairs" % (72 * n / 1e3),
     }
+    if w["method"] == "nlist":
+        info = ctx.nlist_info()
+        hbm_bytes = 144.0 * n + 4.0 * info["entries"] + 32.0 * n  # SURVEY.md 8d + 4 B per stored list entry + packed r
+        roofline["hbm"] = {"bound": "hbm", "achieved": hbm_bytes / (force_ms * 1e-3) / 1e9, "peak": 6545.3, "unit": "GB/s",
+                           "frac": hbm_bytes / (force_ms * 1e-3) / 1e9 / 6545.3, "algorithmic_bytes": hbm_bytes,
+                           "traffic": 515.8e6 if n == 1048576 else None,
+                           "peak_source": "MEASURED_PEAKS.json hbm_gbs",
+                           "note": "fused step kernel: 144 B/atom state + 4 B per list entry (%.1f entries/atom) + 32 B/atom "
+                                   "packed positions; traffic = dram read+write of profiles/r1_ncu_nlist_step_v2.txt" % (info["entries"] / n)}
+        roofline["note"] = ("the fused neighbour-list step is co-limited: L1 tag stage for the position gathers (one 128-byte "
+                            "line per clock per SM, profiles/), HBM for the list stream, FP64 pipe for the pair arithmetic")
+    elif w["method"] == "allpairs":
+        roofline["hbm_note"] = "state is %.1f KB, L2-resident; HBM is not the bound for all-pairs" % (72 * n * R / 1e3)
+        if args.workload == "cfg2":
+            roofline["traffic"] = 203.5e3  # dram read+write per launch, profiles/r1_ncu_d_cfg2_summary.txt (ncu --set full)
 
     # ---- end to end through the drop-in C ABI call with host arrays ---------------------------
     d = ctx.download()
-    host = lj.SimState.from_arrays([a.copy() for a in d.arrays()])
-    for _ in range(5):
-        lj.verlet_step(p, host)
     ke = max(3, min(args.e2e_steps, args.steps))
-    t0 = time.perf_counter()
-    for _ in range(ke):
-        lj.verlet_step(p, host)
-    te = time.perf_counter() - t0
-    e2e = {"value": n * ke * world / te, "unit": "atom-steps/s",
-           "h2d_bytes_per_step": 9 * n * 8, "d2h_bytes_per_step": 9 * n * 8 + 32,
-           "steps": ke, "ms_per_step": 1e3 * te / ke,
-           "api": "ljmd_verlet_step (drop-in for verlet_step, physics/verlet.f90:41): host arrays in/out every step"}
+    if R == 1:
+        host = lj.SimState.from_arrays([a.copy() for a in d.arrays()])
+        for _ in range(5):
+            lj.verlet_step(p, host)
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            lj.verlet_step(p, host)
+        te = time.perf_counter() - t0
+        api = "ljmd_verlet_step (drop-in for verlet_step, physics/verlet.f90:41): host arrays in/out every step"
+    else:  # the reference has no batched call: upload + one resident step + download of all replicas
+        host = lj.SimState.from_arrays([a.copy() for a in d.arrays()])
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            ctx.upload(host)
+            ctx.step(1)
+            host = ctx.download()
+        te = time.perf_counter() - t0
+        api = "ljmd_ctx_upload + ljmd_ctx_step(1) + ljmd_ctx_download of all replicas every step"
+    e2e = {"value": n * R * ke * world / te, "unit": "atom-steps/s",
+           "h2d_bytes_per_step": 9 * n * R * 8, "d2h_bytes_per_step": 9 * n * R * 8 + 32 * R,
+           "steps": ke, "ms_per_step": 1e3 * te / ke, "api": api}
 
     # ---- CPU baseline (bounded sample) --------------------------------------------------------
     cpu = None
@@ -460,11 +489,14 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "n_atoms": n, "box_length": w["L"], "rc": w["rc"],
+        "config": {"workload": args.workload, "n_atoms": n, "replicas_per_gpu": R, "box_length": w["L"], "rc": w["rc"],
                    "dt": w["dt"], "method": w["method"],
-                   "multi_gpu": "replicas only (one independent system per rank)" if world > 1 else "single system",
-                   "l2": "not flushed: the MD state (%.0f KB) is L2/shared-memory resident by construction "
-                         "and re-read every step; the kernel is FP64-pipe bound" % (72 * n / 1e3)},
+                   "multi_gpu": "replicas only (independent systems per rank, no data-path collective)" if world > 1 else
+                                ("single system" if R == 1 else "%d independent replicas on one GPU" % R),
+                   "l2": ("not flushed: the MD state (%.0f KB) is L2/shared-memory resident by construction "
+                          "and re-read every step; the kernel is FP64-pipe bound" % (72 * n * R / 1e3)) if w["method"] == "allpairs"
+                         else "inputs larger than L2: state + neighbour list = %.0f MB, streamed from HBM every step" %
+                              ((96 * n + 300 * n) / 1e6)},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
         "gpu_launches": int(launches), "wall_s": wall,
         "obs_last": [float(x) for x in np.ravel(obs)[:4]],
