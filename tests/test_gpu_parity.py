@@ -387,3 +387,36 @@ def test_sharded_contexts_match_single(lj, O):
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_nve_energy_drift_10k_steps(lj, O):
+    """North star: energy drift over a 10^4-step NVE run statistically indistinguishable from the
+    reference (the shipped configuration, N=500).  The potential is truncated, not shifted
+    (lj_potential_energy.f90:132-140), so E_tot is a jump process (pairs crossing rc) on top of the
+    O(dt^2) integrator fluctuation; the two trajectories decorrelate (chaos), hence statistics."""
+    p_o, st = make_config(O, "cfg1")
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    nsteps = 10000
+    ref = [a.copy() for a in st]
+    _, ref_ser = O.run_steps(p_o, nsteps, ref, want_series=True)
+    with lj.Context(p, method=lj.METHOD_ALLPAIRS) as ctx:
+        ctx.upload(_state(lj, st))
+        ser = ctx.step_series(nsteps)
+    e_gpu, e_ref = ser[:, 0] + ser[:, 1], ref_ser[:, 0] + ref_ser[:, 1]
+    # identical start: the first 50 steps agree to round-off amplification
+    assert np.all(np.abs(e_gpu[:50] - e_ref[:50]) <= 1e-9 * np.abs(e_ref[:50]))
+    # drift = mean of the last 2000 steps minus mean of the first 2000 steps (after the lattice melts)
+    def drift(e):
+        return e[-2000:].mean() - e[1000:3000].mean()
+    def block_std(e):  # fluctuation of 500-step block means: the noise level of `drift`
+        b = e[1000:].reshape(-1, 500).mean(axis=1)
+        return b.std()
+    noise = max(block_std(e_ref), block_std(e_gpu), 1e-6)
+    assert abs(drift(e_gpu) - drift(e_ref)) <= 6.0 * noise, (drift(e_gpu), drift(e_ref), noise)
+    # same fluctuation level (within a factor of 2) and same mean energy (within the noise)
+    r = e_gpu[1000:].std() / e_ref[1000:].std()
+    assert 0.5 < r < 2.0, r
+    assert abs(e_gpu[1000:].mean() - e_ref[1000:].mean()) <= 6.0 * noise
+    # kinetic temperature statistics agree too
+    t_gpu, t_ref = ser[2000:, 1].mean(), ref_ser[2000:, 1].mean()
+    assert abs(t_gpu - t_ref) <= 0.02 * abs(t_ref)

@@ -73,3 +73,21 @@ def test_shard_range_requires_divisibility():
     assert mg.shard_range(1048576, 3, 8) == (393216, 524288)
     with pytest.raises(ValueError):
         mg.shard_range(10, 0, 4)
+
+
+def test_slab_layers_tile_the_box():
+    """Cell-layer ownership of the slab-sharded neighbour-list path: contiguous, disjoint, complete,
+    balanced to within one layer (same rule as slab_layers() in csrc/lj_nlist.cu)."""
+    import importlib
+
+    import ljmd_b200 as lj
+    mg = importlib.import_module(lj.__name__ + ".multi_gpu")
+    for nc in (3, 12, 39, 128):
+        for world in (1, 2, 3, 4, 8):
+            if world > nc:
+                continue
+            spans = [mg.slab_layers(nc, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == nc
+            assert all(spans[r][1] == spans[r + 1][0] for r in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert min(sizes) >= 1 and max(sizes) - min(sizes) <= 1
