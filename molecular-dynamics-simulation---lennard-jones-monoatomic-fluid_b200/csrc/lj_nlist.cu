@@ -105,11 +105,7 @@ __host__ __device__ __forceinline__ size_t nl_entry(size_t stride, int i, int m)
 __device__ __forceinline__ double4 nl_ld_pos(const double4 *p)
 {
     double4 r;
-#ifdef NL_LOAD_CG
-    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-#else
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-#endif
     return r;
 }
 __device__ __forceinline__ void nl_st_pos(double4 *p, double x, double y, double z)
@@ -649,9 +645,9 @@ __global__ void __launch_bounds__(NL_BS, (SH || MODE == 0) ? 768 / NL_BS : 1024 
     if (valid) {
         const size_t ix = i, iy = ix + n, iz = iy + n;
         const double axn = 24.0 * fx, ayn = 24.0 * fy, azn = 24.0 * fz; // lj_potential_energy.f90:189-191
-        double vx = __ldcg(a.v + ix), vy = __ldcg(a.v + iy), vz = __ldcg(a.v + iz);
+        double vx = a.v[ix], vy = a.v[iy], vz = a.v[iz];
         if (MODE == 1) {
-            const double axo = __ldcg(a.a + ix), ayo = __ldcg(a.a + iy), azo = __ldcg(a.a + iz);
+            const double axo = a.a[ix], ayo = a.a[iy], azo = a.a[iz];
             vx = vx + axo * a.sc.dt_half; vy = vy + ayo * a.sc.dt_half; vz = vz + azo * a.sc.dt_half; // verlet.f90:72-74
             vx = vx + axn * a.sc.dt_half; vy = vy + ayn * a.sc.dt_half; vz = vz + azn * a.sc.dt_half; // verlet.f90:86-88
             a.v[ix] = vx; a.v[iy] = vy; a.v[iz] = vz;
@@ -894,12 +890,6 @@ __global__ void nl_clear_viol_kernel(int *flags, NlCtl *ctl)
     const int t = threadIdx.x;
     if (t < LJMD_MAX_RANKS) flags[(ctl->seq & 1) * LJMD_MAX_RANKS + t] &= ~1;
     if (t == 0) ctl->pending_flag &= ~1; // it is published again by the first step after the rebuild
-}
-
-__global__ void nl_spin_kernel(long long cycles)
-{
-    const long long t0 = clock64();
-    while (clock64() - t0 < cycles) { }
 }
 
 // Slab sharding: owned slot ranges of the state arrays <-> a dense [narr][cmax] exchange buffer.
@@ -1237,7 +1227,6 @@ int nlist_gather_orig(ljmd_ctx *c)
 int nlist_canonicalize(ljmd_ctx *c)
 {
     NlistWork &w = c->nw;
-    const int n = c->sc.n;
     const size_t nn = c->nR, bytes = sizeof(double) * nn;
     LJMD_TRY(nlist_gather_orig(c));
     LJMD_CUDA_CHECK(cudaMemcpyAsync(c->rbuf[0], w.alt, 3 * bytes, cudaMemcpyDeviceToDevice, c->stream));
@@ -1433,13 +1422,6 @@ extern "C" int ljmd_ctx_slab_pack(ljmd_ctx *c, double *dev_buf, int32_t cmax, in
     LJMD_CUDA_CHECK(cudaGetDevice(&prev));
     if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
     const NlArgs a = make_args(c, 0);
-    static double *priv = nullptr; // experiments (LJMD_SLAB_PACK_MODE)
-    const int pmode = getenv("LJMD_SLAB_PACK_MODE") ? atoi(getenv("LJMD_SLAB_PACK_MODE")) : 0;
-    if (pmode && !priv) cudaMalloc(&priv, sizeof(double) * 15 * (size_t)c->sc.n);
-    if (pmode == 1) nl_pack_kernel<<<(cmax + 255) / 256, 256, 0, c->stream>>>(a, priv, cmax);
-    else if (pmode == 2) nl_spin_kernel<<<148, 128, 0, c->stream>>>(200000);
-    else if (pmode == 3) cudaMemsetAsync(priv, 0, sizeof(double) * 12 * (size_t)c->sc.n, c->stream);
-    else
     nl_pack_kernel<<<(cmax + 255) / 256, 256, 0, c->stream>>>(a, dev_buf, cmax);
     c->launches++;
     cudaError_t e = cudaGetLastError();
@@ -1494,7 +1476,6 @@ extern "C" int ljmd_ctx_slab_rebuild(ljmd_ctx *c, int32_t force)
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = set_error(LJMD_ERR_CUDA, "ljmd_ctx_slab_rebuild(): %s", cudaGetErrorString(e));
     }
-    if (getenv("LJMD_SLAB_DEVSYNC")) cudaDeviceSynchronize(); // experiment
     unsigned long long *dsum = nullptr;
     if (c->nw.dbg_exec && getenv("LJMD_SLAB_DEBUG_SUM")) { // debug: the permutation must preserve every per-atom value
         cudaMalloc(&dsum, 64);

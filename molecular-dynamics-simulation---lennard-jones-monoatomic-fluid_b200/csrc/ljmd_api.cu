@@ -179,10 +179,6 @@ static int run_steps_nlist(ljmd_ctx *c, int nsteps)
             c->launches += (int64_t)G * 2; // condition kernel + step kernel; rebuilds are added at the next sync
         }
     }
-    if (getenv("LJMD_NL_B2B")) { // experiment: step kernels back to back (valid only while no rebuild is due)
-        for (; done < nsteps; ++done) LJMD_TRY(nlist_enqueue_step_kernel(c));
-        return LJMD_OK;
-    }
     for (; done < nsteps; ++done) LJMD_TRY(nlist_enqueue_step(c));
     return LJMD_OK;
 }

@@ -139,19 +139,12 @@ class SlabRunner:
 
     def gather(self) -> None:
         """Complete state on every rank: pack own slab, one all-gather, unpack."""
-        import os
-        if os.environ.get("LJMD_SLAB_SKIP_GATHER"):  # experiment (only meaningful with one rank)
-            return
         cmax = int(np.max(np.diff(self.bounds)))
         send, recv = self._buffers(cmax)
-        mode = os.environ.get("LJMD_SLAB_GATHER_MODE", "")
         with self.torch.cuda.stream(self.stream):
-            if mode != "nccl_only":
-                self.ctx.slab_pack(send.data_ptr(), cmax)
-            if mode != "pack_only":
-                self.dist.all_gather_into_tensor(recv, send, group=self.group)
-            if mode not in ("pack_only", "nccl_only"):
-                self.ctx.slab_unpack(recv.data_ptr(), cmax)
+            self.ctx.slab_pack(send.data_ptr(), cmax)
+            self.dist.all_gather_into_tensor(recv, send, group=self.group)
+            self.ctx.slab_unpack(recv.data_ptr(), cmax)
 
     def step(self, nsteps: int) -> np.ndarray:
         """nsteps velocity-Verlet steps; returns this rank's observable share of the last step."""
@@ -172,11 +165,6 @@ class SlabRunner:
                     print(f"[slab debug] rank {self.rank}: ranks disagree on progress at step {self.steps}: {rep}", flush=True)
             left -= done
             self.steps += done
-            if os.environ.get("LJMD_SLAB_FORCE_REBUILD") and not halted and left - done > 0:
-                # experiment: rebuild after every chunk although nothing violated the skin
-                self.ctx.slab_rebuild(force=True)
-                self.rebuilds += 1
-                self.bounds = self.ctx.slab_bounds()
             if halted:
                 shadow = os.environ.get("LJMD_SLAB_SHADOW")
                 if shadow:
