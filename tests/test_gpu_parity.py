@@ -420,3 +420,22 @@ def test_nve_energy_drift_10k_steps(lj, O):
     # kinetic temperature statistics agree too
     t_gpu, t_ref = ser[2000:, 1].mean(), ref_ser[2000:, 1].mean()
     assert abs(t_gpu - t_ref) <= 0.02 * abs(t_ref)
+
+
+def test_initial_config_program_sequence_on_gpu(lj, O):
+    """md_initial_config_program.f90:73-116 through the host mirror + the GPU force routine: the
+    shipped run's start (seed -12345, E_target -555) and 20 warm-up steps vs the oracle."""
+    import importlib
+    ic = importlib.import_module(lj.__name__ + ".initial_config")
+    p_o = O.params_init(500, 10.0, 1e-4, 4.9, 5)
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    ref, e_ref, k_ref = O.initial_config(p_o, -12345, -555.0)
+    st, epot, ekin = ic.initial_config(lj, p, seed=-12345, target_total_energy=-555.0)
+    assert abs(epot - e_ref) <= TOL * abs(e_ref) and abs(ekin - k_ref) <= TOL * k_ref
+    assert abs((epot + ekin) + 555.0) <= 1e-10
+    assert np.array_equal(st.rx, ref[0]) and rel_err(st.vx, ref[3]) <= TOL and rel_err(st.vz, ref[5]) <= TOL
+    st2, e2, k2 = ic.initial_config(lj, p, seed=-12345, target_total_energy=-555.0, warmup_steps=20)
+    ref2 = [a.copy() for a in ref]
+    obs = O.run_steps(p_o, 20, ref2)
+    assert abs(e2 - obs[0]) <= 1e-10 * abs(obs[0]) and abs(k2 - obs[1]) <= 1e-10 * abs(obs[1])
+    assert rel_err(st2.rx, ref2[0]) <= 1e-10
