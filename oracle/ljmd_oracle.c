@@ -646,3 +646,104 @@ int orc_verlet_step_cells(const orc_params *p, double *rx, double *ry, double *r
     *ekin = orc_halfkick_ekin(p, vx, vy, vz, ax, ay, az);
     return ORC_OK;
 }
+
+
+/* ---------------------------------------------------------------------------------------
+ * Consumers of the per-step reductions.
+ * stats/md_means.f90:192-275 (md_means_add_sample, virial always present as in
+ * md_simulation_program.f90:366-371), :284-366 (md_means_get), stats/stats_math.f90:56-61,
+ * physics/thermodynamic_coefs.f90:87-205.
+ * Quantity order: U, K, E, T, P, 1/K, dU, ddU, dU/K, dU^2/K, ddU/K.
+ * ------------------------------------------------------------------------------------- */
+void orc_means_init(orc_means *m, int32_t n, double volume)
+{
+    memset(m, 0, sizeof(*m));
+    m->n = n;
+    m->volume = volume;
+}
+
+int orc_means_add(orc_means *m, double epot, double ekin, double virial, double d_epot,
+                  double dd_epot, double *temp_inst, double *press_inst)
+{
+    if (m->n <= 0) return ORC_ERR_N;
+    if (!(m->volume > 0.0)) return ORC_ERR_VOLUME;
+    const double npd = (double)m->n;
+    const double rho = npd / m->volume;
+    const double U = epot, K = ekin;
+    const double E = U + K;
+    const double T = 2.0 * K / (3.0 * npd);                    /* :221 */
+    const double P = rho * T + virial / (3.0 * m->volume);     /* :227 */
+    if (K <= 0.0) return ORC_ERR_EKIN;                         /* :243 */
+    const double Kinv = 1.0 / K;
+    const double dU = d_epot, ddU = dd_epot;
+    const double dU_Kinv = dU * Kinv, ddU_Kinv = ddU * Kinv, dU2_Kinv = (dU * dU) * Kinv;
+    const double x[11] = {U, K, E, T, P, Kinv, dU, ddU, dU_Kinv, dU2_Kinv, ddU_Kinv};
+    m->n_samples += 1;
+    for (int q = 0; q < 11; ++q) {
+        m->sum[q] = m->sum[q] + x[q];
+        m->sum_sq[q] = m->sum_sq[q] + x[q] * x[q];
+    }
+    if (temp_inst) *temp_inst = T;
+    if (press_inst) *press_inst = P;
+    return ORC_OK;
+}
+
+int orc_means_get(const orc_means *m, double *mean, double *std)
+{
+    if (m->n_samples <= 0) return ORC_ERR_N;
+    const double inv_ns = 1.0 / (double)m->n_samples;
+    for (int q = 0; q < 11; ++q) {
+        mean[q] = m->sum[q] * inv_ns;
+        const double m2 = m->sum_sq[q] * inv_ns;
+        const double var = m2 - mean[q] * mean[q];             /* stats_math.f90:60 */
+        std[q] = sqrt(var > 0.0 ? var : 0.0);
+    }
+    return ORC_OK;
+}
+
+/* out[16] = temperature, pressure, Ca_v, Ce_v, gamma, K_S_aux, K_S, K_S_inv, K_T, K_T_inv, Ca_p,
+ * Ce_p, alpha_E1, alpha_E2, alpha_S, alpha_P.  Returns ORC_ERR_EKIN where the reference stops on a
+ * vanishing denominator. */
+int orc_thermo_coefs(const orc_params *p, double ekin_mean, double press_mean,
+                     double ekinInv_mean, double d_epot_mean, double dd_epot_mean,
+                     double d_epot_ekinInv_mean, double d_epot2_ekinInv_mean, double *out)
+{
+    const double npd = (double)p->n;
+    const double f = 3.0 * npd - 3.0;                          /* :105 */
+    if (f <= 0.0) return ORC_ERR_N;
+    const double aux1 = 1.0 - 2.0 / f, aux2 = f / 2.0 - 1.0;   /* :109-110 */
+    const double V = p->volume;
+    const double T = 2.0 * ekin_mean / f;                      /* :118 */
+    const double P = press_mean;
+    double denom = 1.0 - aux1 * ekin_mean * ekinInv_mean;      /* :128 */
+    if (fabs(denom) < 1.0e-14) return ORC_ERR_EKIN;
+    const double Ca_v = 1.0 / denom;
+    const double Ce_v = Ca_v / npd;
+    if (fabs(Ce_v) < 1.0e-14) return ORC_ERR_EKIN;
+    const double gamma = 1.0 / Ce_v + (aux2 / 3.0) * (d_epot_mean * ekinInv_mean - d_epot_ekinInv_mean); /* :137 */
+    const double K_S_aux = ((npd * T * (1.0 + 2.0 * gamma - 1.0 / Ce_v)) / V) +
+                           (dd_epot_mean - 2.0 * d_epot_mean) / (9.0 * V);                                /* :163 */
+    const double K_S = K_S_aux - (aux2 * (d_epot2_ekinInv_mean - 2.0 * d_epot_mean * d_epot_ekinInv_mean +
+                                          (d_epot_mean * d_epot_mean) * ekinInv_mean)) / (9.0 * V * V);  /* :164 */
+    if (fabs(K_S) < 1.0e-14) return ORC_ERR_EKIN;
+    const double K_S_inv = 1.0 / K_S;
+    const double K_T = K_S - (T * Ca_v * (gamma * gamma)) / V; /* :172 */
+    if (fabs(K_T) < 1.0e-14) return ORC_ERR_EKIN;
+    const double K_T_inv = 1.0 / K_T;
+    const double Ca_p = Ca_v * (K_S / K_T);
+    const double Ce_p = Ca_p / npd;
+    denom = (P * V / Ca_v) - (gamma * T);                      /* :188 */
+    if (fabs(denom) < 1.0e-14) return ORC_ERR_EKIN;
+    const double alpha_E1 = 1.0 / denom;
+    denom = (1.0 / 3.0) * (aux1 * ekin_mean * d_epot_ekinInv_mean - d_epot_mean); /* :193 */
+    if (fabs(denom) < 1.0e-14) return ORC_ERR_EKIN;
+    const double alpha_E2 = 1.0 / denom;
+    denom = gamma * T;
+    if (fabs(denom) < 1.0e-14) return ORC_ERR_EKIN;
+    const double alpha_S = -1.0 / denom;
+    const double alpha_P = (Ca_v * gamma) / V * K_T_inv;       /* :203 */
+    const double r[16] = {T, P, Ca_v, Ce_v, gamma, K_S_aux, K_S, K_S_inv, K_T, K_T_inv,
+                          Ca_p, Ce_p, alpha_E1, alpha_E2, alpha_S, alpha_P};
+    for (int q = 0; q < 16; ++q) out[q] = r[q];
+    return ORC_OK;
+}

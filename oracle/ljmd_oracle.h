@@ -163,6 +163,26 @@ int orc_verlet_step_cells(const orc_params *p, double *rx, double *ry, double *r
                           double *vy, double *vz, double *ax, double *ay, double *az,
                           double *epot, double *ekin, double *d_epot, double *dd_epot);
 
+/* ---------------------------------------------------------------------------------------
+ * Consumers of the per-step reductions: stats/md_means.f90:192-366, stats/stats_math.f90:56-61,
+ * physics/thermodynamic_coefs.f90:87-205.  Quantity order of sum / sum_sq / mean / std:
+ * U, K, E, T, P, 1/K, dU, ddU, dU/K, dU^2/K, ddU/K.
+ * ------------------------------------------------------------------------------------- */
+typedef struct orc_means {
+    int32_t n, n_samples;
+    double volume;
+    double sum[11], sum_sq[11];
+} orc_means;
+void orc_means_init(orc_means *m, int32_t n, double volume);
+int orc_means_add(orc_means *m, double epot, double ekin, double virial, double d_epot,
+                  double dd_epot, double *temp_inst, double *press_inst);
+int orc_means_get(const orc_means *m, double *mean11, double *std11);
+/* out[16] = temperature, pressure, Ca_v, Ce_v, gamma, K_S_aux, K_S, K_S_inv, K_T, K_T_inv, Ca_p, Ce_p,
+ * alpha_E1, alpha_E2, alpha_S, alpha_P */
+int orc_thermo_coefs(const orc_params *p, double ekin_mean, double press_mean,
+                     double ekinInv_mean, double d_epot_mean, double dd_epot_mean,
+                     double d_epot_ekinInv_mean, double d_epot2_ekinInv_mean, double *out16);
+
 #ifdef __cplusplus
 }
 #endif

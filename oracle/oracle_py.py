@@ -233,3 +233,34 @@ def neighbor_list(p: OrcParams, rng: float, rx, ry, rz, cap: int):
     _chk(lib().orc_neighbor_list(C.byref(p), C.c_double(rng), _p(rx), _p(ry), _p(rz), cap,
                                  _ip(counts), _ip(nbr)))
     return counts, nbr
+
+
+class OrcMeans(C.Structure):
+    _fields_ = [("n", C.c_int32), ("n_samples", C.c_int32), ("volume", C.c_double),
+                ("sum", C.c_double * 11), ("sum_sq", C.c_double * 11)]
+
+
+class Means:
+    """stats/md_means.f90:192-366 (virial always present)."""
+
+    def __init__(self, n: int, volume: float):
+        self.m = OrcMeans()
+        lib().orc_means_init(C.byref(self.m), n, C.c_double(volume))
+
+    def add(self, epot, ekin, virial, d_epot, dd_epot):
+        t, p = C.c_double(), C.c_double()
+        _chk(lib().orc_means_add(C.byref(self.m), C.c_double(epot), C.c_double(ekin), C.c_double(virial),
+                                 C.c_double(d_epot), C.c_double(dd_epot), C.byref(t), C.byref(p)))
+        return t.value, p.value
+
+    def get(self):
+        mean, std = np.zeros(11), np.zeros(11)
+        _chk(lib().orc_means_get(C.byref(self.m), _p(mean), _p(std)))
+        return mean, std
+
+
+def thermo_coefs(p: OrcParams, ekin_mean, press_mean, ekinInv_mean, d_mean, dd_mean, d_kinv_mean, d2_kinv_mean):
+    out = np.zeros(16)
+    _chk(lib().orc_thermo_coefs(C.byref(p), *[C.c_double(x) for x in (ekin_mean, press_mean, ekinInv_mean, d_mean,
+                                                                      dd_mean, d_kinv_mean, d2_kinv_mean)], _p(out)))
+    return out

@@ -439,3 +439,34 @@ def test_initial_config_program_sequence_on_gpu(lj, O):
     obs = O.run_steps(p_o, 20, ref2)
     assert abs(e2 - obs[0]) <= 1e-10 * abs(obs[0]) and abs(k2 - obs[1]) <= 1e-10 * abs(obs[1])
     assert rel_err(st2.rx, ref2[0]) <= 1e-10
+
+
+def test_replica_ensemble_end_to_end(lj, O):
+    """Config 5 in miniature: 4 replicas (velocity seeds -(12345+r)), batched in one
+    context, sampled every 100 steps after 100 warm-up steps; per-replica means -> thermodynamic
+    coefficients -> ensemble mean / population std, against the same pipeline driven by the oracle."""
+    import importlib
+    ob = importlib.import_module(lj.__name__ + ".observables")
+    p_o = O.params_init(500, 10.0, 1e-4, 4.9, 5)
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    R, total, interval, warm = 4, 400, 100, 100
+    states, coefs_ref = [], []
+    for r in range(R):
+        s_r, _, _ = O.initial_config(p_o, -(12345 + r), -555.0)
+        states.append(lj.SimState.from_arrays([a.copy() for a in s_r]))
+        ref = [a.copy() for a in s_r]
+        acc = O.Means(500, p_o.volume)
+        for step in range(interval, total + 1, interval):
+            obs = O.run_steps(p_o, interval, ref)
+            if step > warm:
+                acc.add(obs[0], obs[1], -obs[2], obs[2], obs[3])
+        m, _ = acc.get()
+        mm = dict(zip(ob.QUANTITIES, m))
+        coefs_ref.append(O.thermo_coefs(p_o, mm["K"], mm["P"], mm["Kinv"], mm["dU"], mm["ddU"], mm["dU_Kinv"], mm["dU2_Kinv"]))
+    coefs_ref = np.array(coefs_ref)                      # [R][16]
+    out = ob.run_ensemble(lj, p, states, total, interval, warm)
+    assert out["n_replicas"] == R and out["n_samples"] == 3
+    mean_ref, std_ref = coefs_ref.mean(axis=0), coefs_ref.std(axis=0)
+    for k, name in enumerate(ob.COEFS):
+        assert abs(out["mean"][name] - mean_ref[k]) <= 1e-7 * abs(mean_ref[k]), name
+        assert abs(out["std"][name] - std_ref[k]) <= 1e-5 * abs(mean_ref[k]) + 1e-12, name
