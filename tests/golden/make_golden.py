@@ -56,6 +56,18 @@ def main():
         obs_cells=np.array(fc[3:6]), n_cand=fc[6], n_cut=fc[7], cell=cell, start=start,
         order=order,
     )
+    # neighbour-list fixture of the same state: cells with edge >= rc + skin (skin 0.3) and the full
+    # Verlet list within 2.8 (original numbering, ascending); does NOT rewrite cells_n864.npz's state
+    g = np.load(os.path.join(HERE, "cells_n864.npz"))
+    s = [np.ascontiguousarray(a) for a in g["state300"]]
+    rng = 2.5 + 0.3
+    cell = O.cell_assign_range(p, rng, *s[:3])
+    start, order = O.cell_sort_range(p, rng, cell)
+    counts, nbr = O.neighbor_list(p, rng, *s[:3], cap=144)
+    np.savez_compressed(
+        os.path.join(HERE, "nlist_n864.npz"),
+        range=rng, cell=cell, start=start, order=order, counts=counts, nbr=nbr.astype(np.int16),
+    )
     print("golden fixtures written to", HERE)
 
 

@@ -82,6 +82,26 @@ def test_nlist_forces_and_integers_n864(lj, O):
         assert np.array_equal(getattr(got, name), s[k]), name
 
 
+def test_nlist_golden_n864(lj):
+    """Cells (edge >= rc+skin) and neighbour sets against the committed fixture -- no oracle at test time."""
+    g, gn = np.load(os.path.join(GOLD, "cells_n864.npz")), np.load(os.path.join(GOLD, "nlist_n864.npz"))
+    p = lj.init_params(864, float(g["L"]), 1e-3, 2.5, 6)
+    s = [np.ascontiguousarray(a) for a in g["state300"]]
+    with lj.Context(p, method=lj.METHOD_NLIST) as ctx:
+        ctx.upload(_state(lj, s))
+        obs = ctx.compute_forces()
+        got = ctx.download(("ax", "ay", "az"))
+        cell, start, order = ctx.download_cells()
+        counts, nbr = ctx.download_nlist()
+    assert np.array_equal(cell, gn["cell"]) and np.array_equal(start, gn["start"]) and np.array_equal(order, gn["order"])
+    assert np.array_equal(counts, gn["counts"])
+    assert np.array_equal(nbr[:, :144], gn["nbr"].astype(np.int32)[:, :nbr.shape[1]])
+    for k, name in enumerate(("ax", "ay", "az")):
+        assert rel_err(getattr(got, name), g["acc"][k]) <= TOL
+    for g_, w_ in zip(obs, g["obs"]):
+        assert abs(g_ - w_) <= TOL * abs(w_)
+
+
 def test_nlist_vs_oracle_32k(lj, O):
     p_o, st = make_config(O, "cfg3")
     s = melt(O, p_o, st, 20, cells=True)

@@ -203,3 +203,18 @@ def test_cell_binning_wraps_out_of_box_input(O):
     y = np.full(864, 1.0)
     cell = O.cell_assign(p, x, y, y.copy())
     assert cell[0] == cell[1] == cell[2] == cell[3]
+
+
+def test_golden_nlist_n864(O):
+    """The committed neighbour-list fixture (tests/golden/make_golden.py) against the oracle."""
+    import os
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    g, gn = np.load(os.path.join(here, "cells_n864.npz")), np.load(os.path.join(here, "nlist_n864.npz"))
+    p = O.params_init(864, float(g["L"]), 1e-3, 2.5, 6)
+    s = [np.ascontiguousarray(a) for a in g["state300"]]
+    rng = float(gn["range"])
+    cell = O.cell_assign_range(p, rng, *s[:3])
+    start, order = O.cell_sort_range(p, rng, cell)
+    counts, nbr = O.neighbor_list(p, rng, *s[:3], cap=144)
+    assert np.array_equal(cell, gn["cell"]) and np.array_equal(start, gn["start"]) and np.array_equal(order, gn["order"])
+    assert np.array_equal(counts, gn["counts"]) and np.array_equal(nbr, gn["nbr"].astype(np.int32))
