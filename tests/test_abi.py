@@ -101,3 +101,26 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in txt.lower().replace("no cpu fallback", ""), (dirpath, f)
+
+
+def test_cpp_host_links_and_fails_loudly_without_gpu(lj, tmp_path):
+    """examples/md_driver.cpp: a C++ host on the C ABI alone (no torch, no Python).  It must compile
+    and link against include/ljmd.h + libljmd.so; on a machine without a CUDA device it must stop with
+    the library's status instead of computing anything on the CPU; bad parameters stop with the
+    reference's message (md_types.f90:152)."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(lj.LIB_PATH)
+    exe = os.path.join(tmp_path, "md_driver")
+    subprocess.run(["g++", "-O2", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "md_driver.cpp"),
+                    "-L" + libdir, "-lljmd", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    bad = subprocess.run([exe, "5", "10", "5.0"], capture_output=True, text=True)
+    assert bad.returncode == 7 and "must be < L/2" in bad.stderr
+    run = subprocess.run([exe, "3", "6.0", "2.5", "1e-3", "40", "20", "0"], capture_output=True, text=True)
+    if lj.device_count() == 0:
+        assert run.returncode == 100 and "no CPU fallback" in run.stderr
+    else:
+        assert run.returncode == 0 and run.stdout.count("\n") >= 4
