@@ -484,8 +484,11 @@ __device__ __forceinline__ void nl_pair(double xi, double yi, double zi, const d
 // ring of NL_PF groups is kept in flight); the packed positions are gathered from L1/L2.
 constexpr int NL_PF = 3;
 
-template <bool MIC>
-__device__ __forceinline__ void nl_walk(const int4 *__restrict__ nb, size_t stride, int cnt,
+// TPA lanes share one atom: lane `sub` takes the entry groups sub, sub+TPA, ... (TPA = 4 gives small
+// systems -- and the slabs of a sharded run -- four times as many threads; the lane partials are
+// combined afterwards in a fixed butterfly order).
+template <bool MIC, int TPA>
+__device__ __forceinline__ void nl_walk(const int4 *__restrict__ nb, size_t stride, int cnt, int sub,
                                         const double4 *__restrict__ pos, double xi, double yi, double zi, double L,
                                         double invL, double rc2, double &fx, double &fy, double &fz, double &s12,
                                         double &s6)
@@ -495,14 +498,14 @@ __device__ __forceinline__ void nl_walk(const int4 *__restrict__ nb, size_t stri
 #pragma unroll
     for (int u = 0; u < NL_PF; ++u) {
         ring[u] = make_int4(0, 0, 0, 0);
-        if (u < ngrp) ring[u] = __ldcs(nb + (size_t)u * stride);
+        if (sub + u * TPA < ngrp) ring[u] = __ldcs(nb + (size_t)(sub + u * TPA) * stride);
     }
-    int g = 0;
-    for (; g < nfull; ++g) {
+    int g = sub;
+    for (; g < nfull; g += TPA) {
         const int4 j = ring[0];
 #pragma unroll
         for (int u = 0; u + 1 < NL_PF; ++u) ring[u] = ring[u + 1];
-        if (g + NL_PF < ngrp) ring[NL_PF - 1] = __ldcs(nb + (size_t)(g + NL_PF) * stride);
+        if (g + NL_PF * TPA < ngrp) ring[NL_PF - 1] = __ldcs(nb + (size_t)(g + NL_PF * TPA) * stride);
         const double4 pa = nl_ld_pos(pos + j.x), pb = nl_ld_pos(pos + j.y), pc = nl_ld_pos(pos + j.z),
                       pd = nl_ld_pos(pos + j.w);
         nl_pair<MIC, false>(xi, yi, zi, pa, true, L, invL, rc2, fx, fy, fz, s12, s6);
@@ -510,7 +513,7 @@ __device__ __forceinline__ void nl_walk(const int4 *__restrict__ nb, size_t stri
         nl_pair<MIC, false>(xi, yi, zi, pc, true, L, invL, rc2, fx, fy, fz, s12, s6);
         nl_pair<MIC, false>(xi, yi, zi, pd, true, L, invL, rc2, fx, fy, fz, s12, s6);
     }
-    if (g < ngrp) { // last, partly filled group: padding entries point at the atom itself and are masked
+    if (g < ngrp) { // this lane owns the last, partly filled group: padding entries point at the atom itself and are masked
         const int4 j = ring[0];
         const int rem = cnt & 3;
         const double4 pa = nl_ld_pos(pos + j.x), pb = nl_ld_pos(pos + j.y), pc = nl_ld_pos(pos + j.z);
@@ -577,14 +580,16 @@ __device__ __forceinline__ void nl_st_release_sys(int *p, int v)
 // Single-GPU variants: <= 64 registers (32 warps per SM hide the gather latency).  The sharded
 // variants need a few more registers; they get up to 85 rather than being squeezed into 64 with
 // local-memory spills.
-template <int MODE, bool TRACK, bool SH>
-__global__ void __launch_bounds__(NL_BS, (SH || MODE == 0) ? 768 / NL_BS : 1024 / NL_BS) nl_step_kernel(NlArgs a)
+template <int MODE, bool TRACK, bool SH, int TPA>
+__global__ void __launch_bounds__(NL_BS, TPA > 1 ? 640 / NL_BS : (SH || MODE == 0) ? 768 / NL_BS : 1024 / NL_BS) nl_step_kernel(NlArgs a)
 {
     __shared__ double scratch[5 * (NL_BS / 32)];
     __shared__ bool is_last;
     __shared__ int s_viol;
+    constexpr int APB = NL_BS / TPA; // atoms per CTA
     const int n = a.sc.n;
-    int i = blockIdx.x * NL_BS + threadIdx.x;
+    const int sub = threadIdx.x % TPA;
+    int i = blockIdx.x * APB + threadIdx.x / TPA;
     bool valid = i < n;
     int nact = gridDim.x, seq = 0, sb = 0, se = n;
     if (SH) {
@@ -610,13 +615,13 @@ __global__ void __launch_bounds__(NL_BS, (SH || MODE == 0) ? 768 / NL_BS : 1024 
         const int layer = a.nc * a.nc;
         sb = a.cell_start[a.xlo * layer];
         se = a.cell_start[a.xhi * layer];
-        nact = (se - sb + NL_BS - 1) / NL_BS;
+        nact = (se - sb + APB - 1) / APB;
         if (nact > (int)gridDim.x) { // more owned atoms than the launch has CTAs for: flagged, reported by the host
             if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(&a.ctl->overflow, 0x40000000);
             nact = gridDim.x;
         }
         if ((int)blockIdx.x >= nact) return;
-        i = sb + blockIdx.x * NL_BS + threadIdx.x;
+        i = sb + blockIdx.x * APB + threadIdx.x / TPA;
         valid = i < se;
         if (a.dbg_exec && threadIdx.x == 0 && seq < 4096) atomicAdd(&a.dbg_exec[seq], 1);
     }
@@ -637,12 +642,20 @@ __global__ void __launch_bounds__(NL_BS, (SH || MODE == 0) ? 768 / NL_BS : 1024 
     const bool fast = __all_sync(0xffffffffu, inter) && (a.ctl->unwrapped == 0);
     double fx = 0.0, fy = 0.0, fz = 0.0, s12 = 0.0, s6 = 0.0;
     const int4 *nb = reinterpret_cast<const int4 *>(a.nbr) + i;
-    if (fast) nl_walk<false>(nb, a.stride, cnt, pos, xi, yi, zi, L, invL, rc2, fx, fy, fz, s12, s6);
-    else nl_walk<true>(nb, a.stride, cnt, pos, xi, yi, zi, L, invL, rc2, fx, fy, fz, s12, s6);
+    if (fast) nl_walk<false, TPA>(nb, a.stride, cnt, sub, pos, xi, yi, zi, L, invL, rc2, fx, fy, fz, s12, s6);
+    else nl_walk<true, TPA>(nb, a.stride, cnt, sub, pos, xi, yi, zi, L, invL, rc2, fx, fy, fz, s12, s6);
+    if (TPA > 1) { // force partials of the TPA lanes of an atom, fixed butterfly order
+#pragma unroll
+        for (int o = 1; o < TPA; o <<= 1) {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o);
+            fy += __shfl_xor_sync(0xffffffffu, fy, o);
+            fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        }
+    }
 
-    double s[5] = {s12, s6, 0.0, 0.0, 0.0};
+    double s[5] = {s12, s6, 0.0, 0.0, 0.0}; // every lane contributes its own share of the pair sums
     double d2 = 0.0;
-    if (valid) {
+    if (valid && sub == 0) {
         const size_t ix = i, iy = ix + n, iz = iy + n;
         const double axn = 24.0 * fx, ayn = 24.0 * fy, azn = 24.0 * fz; // lj_potential_energy.f90:189-191
         double vx = a.v[ix], vy = a.v[iy], vz = a.v[iz];
@@ -702,7 +715,7 @@ __global__ void __launch_bounds__(NL_BS, (SH || MODE == 0) ? 768 / NL_BS : 1024 
 
     // fixed-order reduction of all CTA partials
     double r[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int b = threadIdx.x; b < (SH ? nact : a.nblk); b += NL_BS) {
+    for (int b = threadIdx.x; b < (SH ? nact : (int)gridDim.x); b += NL_BS) {
 #pragma unroll
         for (int q = 0; q < 5; ++q) r[q] += __ldcg(a.spart + (size_t)b * 5 + q);
     }
@@ -997,6 +1010,10 @@ int nlist_plan(ljmd_ctx *c)
     w.maxnb = (cap + 3) / 4 * 4;
     w.stride = ((size_t)n + 31) / 32 * 32;
     w.nblk = (n + NL_BS - 1) / NL_BS;
+    // lanes per atom of the step kernel: 4 is opt-in (LJMD_NL_TPA=4): measured no gain at N=32k on one GPU
+    // (30.0 vs 28.0 us); meant for the small slabs of 8-GPU runs, not yet measured there
+    w.tpa = 1;
+    if (const char *e = getenv("LJMD_NL_TPA")) w.tpa = (atoi(e) == 4) ? 4 : 1;
     w.narr = c->st.rux ? 15 : 12;
     // work units: runs of about NL_BS atoms along z inside one cell column
     const double apc = (double)n / w.ncells; // atoms per cell
@@ -1030,7 +1047,7 @@ int nlist_plan(ljmd_ctx *c)
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.p4, 0, sizeof(double4) * 2 * (size_t)n, c->stream));
     LJMD_CUDA_CHECK(cudaMalloc(&w.r0, sizeof(double) * 3 * (size_t)n));
     LJMD_CUDA_CHECK(cudaMalloc(&w.alt, sizeof(double) * 15 * (size_t)n));
-    LJMD_CUDA_CHECK(cudaMalloc(&w.spart, sizeof(double) * 5 * (size_t)w.nblk));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.spart, sizeof(double) * 5 * 4 * (size_t)w.nblk)); // room for 4 lanes per atom
     LJMD_CUDA_CHECK(cudaMalloc(&w.ctl, sizeof(NlCtl)));
     LJMD_CUDA_CHECK(cudaMalloc(&w.flags, sizeof(int) * 2 * LJMD_MAX_RANKS));
     if (getenv("LJMD_SLAB_DEBUG")) {
@@ -1044,7 +1061,7 @@ int nlist_plan(ljmd_ctx *c)
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.nb_cnt, 0, sizeof(int) * (size_t)n, c->stream));
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.interior, 0, (size_t)n, c->stream));
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.r0, 0, sizeof(double) * 3 * (size_t)n, c->stream));
-    LJMD_CUDA_CHECK(cudaMemsetAsync(w.spart, 0, sizeof(double) * 5 * (size_t)w.nblk, c->stream));
+    LJMD_CUDA_CHECK(cudaMemsetAsync(w.spart, 0, sizeof(double) * 5 * 4 * (size_t)w.nblk, c->stream));
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.ctl, 0, sizeof(NlCtl), c->stream));
     nl_identity_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, w.orig, w.slot_of_orig);
     LJMD_CUDA_CHECK(cudaGetLastError());
@@ -1109,7 +1126,8 @@ int nlist_enqueue_forces(ljmd_ctx *c)
 {
     LJMD_TRY(nlist_enqueue_rebuild(c, 0));
     const NlArgs a = make_args(c, 0);
-    nl_step_kernel<0, false, false><<<c->nw.nblk, NL_BS, 0, c->stream>>>(a);
+    if (c->nw.tpa == 4) nl_step_kernel<0, false, false, 4><<<(c->sc.n + NL_BS / 4 - 1) / (NL_BS / 4), NL_BS, 0, c->stream>>>(a);
+    else nl_step_kernel<0, false, false, 1><<<c->nw.nblk, NL_BS, 0, c->stream>>>(a);
     if (!c->capturing) c->launches++;
     LJMD_CUDA_CHECK(cudaGetLastError());
     return LJMD_OK;
@@ -1127,12 +1145,18 @@ int nlist_enqueue_drift(ljmd_ctx *c)
 int nlist_enqueue_step_kernel(ljmd_ctx *c)
 {
     const NlArgs a = make_args(c, 1);
+    const bool track = c->st.rux != nullptr;
+    const int tpa = c->nw.tpa;
+    const int grid = c->nw.sh_on ? c->nw.own_blocks : (c->sc.n + NL_BS / tpa - 1) / (NL_BS / tpa);
+#define LJMD_NL_LAUNCH(TR, SHD, T) nl_step_kernel<1, TR, SHD, T><<<grid, NL_BS, 0, c->stream>>>(a)
     if (c->nw.sh_on) {
-        const int grid = c->nw.own_blocks;
-        if (c->st.rux) nl_step_kernel<1, true, true><<<grid, NL_BS, 0, c->stream>>>(a);
-        else nl_step_kernel<1, false, true><<<grid, NL_BS, 0, c->stream>>>(a);
-    } else if (c->st.rux) nl_step_kernel<1, true, false><<<c->nw.nblk, NL_BS, 0, c->stream>>>(a);
-    else nl_step_kernel<1, false, false><<<c->nw.nblk, NL_BS, 0, c->stream>>>(a);
+        if (tpa == 4) { if (track) LJMD_NL_LAUNCH(true, true, 4); else LJMD_NL_LAUNCH(false, true, 4); }
+        else { if (track) LJMD_NL_LAUNCH(true, true, 1); else LJMD_NL_LAUNCH(false, true, 1); }
+    } else {
+        if (tpa == 4) { if (track) LJMD_NL_LAUNCH(true, false, 4); else LJMD_NL_LAUNCH(false, false, 4); }
+        else { if (track) LJMD_NL_LAUNCH(true, false, 1); else LJMD_NL_LAUNCH(false, false, 1); }
+    }
+#undef LJMD_NL_LAUNCH
     if (!c->capturing) c->launches++;
     LJMD_CUDA_CHECK(cudaGetLastError());
     c->nw.cur_host ^= 1;
@@ -1382,8 +1406,9 @@ extern "C" int ljmd_ctx_slab_attach(ljmd_ctx *c, int32_t rank, int32_t world, co
         slab_layers(w.nc, rank, world, &w.xlo, &w.xhi);
         // CTAs of the step kernel: room for 30 % more atoms than the mean slab (+ one layer's worth)
         const double mean = (double)c->sc.n * (w.xhi - w.xlo) / w.nc;
-        w.own_blocks = (int)((1.3 * mean + 4096.0) / NL_BS) + 1;
-        if (w.own_blocks > w.nblk) w.own_blocks = w.nblk;
+        const int apb = NL_BS / w.tpa;
+        w.own_blocks = (int)((1.3 * mean + 4096.0) / apb) + 1;
+        if (w.own_blocks > w.nblk * w.tpa) w.own_blocks = w.nblk * w.tpa;
         if (c->graph_chunk) { cudaGraphExecDestroy(c->graph_chunk); c->graph_chunk = nullptr; }
         int zero4[5] = {0, 0, 0, 0, 0}; // halted, steps_left, steps_done, seq, pending_flag
         cudaError_t e = cudaMemcpyAsync(reinterpret_cast<char *>(w.ctl) + offsetof(NlCtl, halted), zero4, sizeof(zero4),
@@ -1613,7 +1638,7 @@ extern "C" int ljmd_ctx_slab_run(ljmd_ctx *c, int32_t max_steps, int32_t *steps_
         cudaMemcpy(hcount, w.dbg_exec, sizeof(hcount), cudaMemcpyDeviceToHost);
         const int nact_expect = (h.seq > 0) ? hcount[0] : 0; (void)nact_expect;
         for (int q = 0; q < 4096 && q < h.seq + 2; ++q)
-            if (hcount[q] != 0 && (hcount[q] < w.own_blocks * 3 / 4 - 2000 || hcount[q] > w.nblk))
+            if (hcount[q] != 0 && (hcount[q] < w.own_blocks * 3 / 4 - 2000 || hcount[q] > w.nblk * 4))
                 fprintf(stderr, "[ljmd slab debug] rank %d: step seq %d executed by %d CTAs\n", w.rank, q, hcount[q]);
         if (getenv("LJMD_SLAB_DEBUG_DUMP")) {
             fprintf(stderr, "[ljmd slab debug] exec counts up to seq %d:", h.seq);
