@@ -523,6 +523,48 @@ __device__ __forceinline__ void nl_walk(const int4 *__restrict__ nb, size_t stri
     }
 }
 
+// The same walk with the position gathers of the NEXT group issued before the current group is
+// evaluated (software pipelining; identical arithmetic and summation order).  Small systems have
+// few warps per SM and are bound by the gather round trip (~2000 clocks per group at N=32k,
+// profiles/r1_ncu_nlist_step_cfg3.txt), so they can afford the extra registers.
+template <bool MIC>
+__device__ __forceinline__ void nl_walk_pipe(const int4 *__restrict__ nb, size_t stride, int cnt,
+                                             const double4 *__restrict__ pos, double xi, double yi, double zi,
+                                             double L, double invL, double rc2, double &fx, double &fy, double &fz,
+                                             double &s12, double &s6)
+{
+    const int ngrp = (cnt + 3) >> 2, nfull = cnt >> 2;
+    if (ngrp == 0) return;
+    const int4 zero = make_int4(0, 0, 0, 0);
+    int4 j = __ldcs(nb);
+    int4 jn1 = (1 < ngrp) ? __ldcs(nb + stride) : zero;
+    int4 jn2 = (2 < ngrp) ? __ldcs(nb + 2 * stride) : zero;
+    double4 pa = nl_ld_pos(pos + j.x), pb = nl_ld_pos(pos + j.y), pc = nl_ld_pos(pos + j.z), pd = nl_ld_pos(pos + j.w);
+    for (int g = 0;; ++g) {
+        const bool has_next = g + 1 < ngrp;
+        double4 qa = pa, qb = pb, qc = pc, qd = pd;
+        int4 jn3 = zero;
+        if (has_next) { // every entry of a group is a valid slot (padding = the atom itself)
+            qa = nl_ld_pos(pos + jn1.x); qb = nl_ld_pos(pos + jn1.y); qc = nl_ld_pos(pos + jn1.z); qd = nl_ld_pos(pos + jn1.w);
+            if (g + 3 < ngrp) jn3 = __ldcs(nb + (size_t)(g + 3) * stride);
+        }
+        if (g < nfull) {
+            nl_pair<MIC, false>(xi, yi, zi, pa, true, L, invL, rc2, fx, fy, fz, s12, s6);
+            nl_pair<MIC, false>(xi, yi, zi, pb, true, L, invL, rc2, fx, fy, fz, s12, s6);
+            nl_pair<MIC, false>(xi, yi, zi, pc, true, L, invL, rc2, fx, fy, fz, s12, s6);
+            nl_pair<MIC, false>(xi, yi, zi, pd, true, L, invL, rc2, fx, fy, fz, s12, s6);
+        } else {
+            const int rem = cnt & 3;
+            nl_pair<MIC, true>(xi, yi, zi, pa, rem > 0, L, invL, rc2, fx, fy, fz, s12, s6);
+            nl_pair<MIC, true>(xi, yi, zi, pb, rem > 1, L, invL, rc2, fx, fy, fz, s12, s6);
+            nl_pair<MIC, true>(xi, yi, zi, pc, rem > 2, L, invL, rc2, fx, fy, fz, s12, s6);
+        }
+        if (!has_next) break;
+        pa = qa; pb = qb; pc = qc; pd = qd;
+        jn1 = jn2; jn2 = jn3;
+    }
+}
+
 __device__ __forceinline__ double nl_drift_wrap(double x, double v, double acc, const SimConst &sc)
 {
     const double xn = (x + v * sc.dt) + acc * sc.dt_square_half; // verlet.f90:58
@@ -580,8 +622,9 @@ __device__ __forceinline__ void nl_st_release_sys(int *p, int v)
 // Single-GPU variants: <= 64 registers (32 warps per SM hide the gather latency).  The sharded
 // variants need a few more registers; they get up to 85 rather than being squeezed into 64 with
 // local-memory spills.
-template <int MODE, bool TRACK, bool SH, int TPA>
-__global__ void __launch_bounds__(NL_BS, TPA > 1 ? 640 / NL_BS : (SH || MODE == 0) ? 768 / NL_BS : 1024 / NL_BS) nl_step_kernel(NlArgs a)
+template <int MODE, bool TRACK, bool SH, int TPA, bool PIPE = false>
+__global__ void __launch_bounds__(NL_BS, PIPE ? 512 / NL_BS : TPA > 1 ? 640 / NL_BS : (SH || MODE == 0) ? 768 / NL_BS : 1024 / NL_BS)
+nl_step_kernel(NlArgs a)
 {
     __shared__ double scratch[5 * (NL_BS / 32)];
     __shared__ bool is_last;
@@ -642,8 +685,13 @@ __global__ void __launch_bounds__(NL_BS, TPA > 1 ? 640 / NL_BS : (SH || MODE == 
     const bool fast = __all_sync(0xffffffffu, inter) && (a.ctl->unwrapped == 0);
     double fx = 0.0, fy = 0.0, fz = 0.0, s12 = 0.0, s6 = 0.0;
     const int4 *nb = reinterpret_cast<const int4 *>(a.nbr) + i;
-    if (fast) nl_walk<false, TPA>(nb, a.stride, cnt, sub, pos, xi, yi, zi, L, invL, rc2, fx, fy, fz, s12, s6);
-    else nl_walk<true, TPA>(nb, a.stride, cnt, sub, pos, xi, yi, zi, L, invL, rc2, fx, fy, fz, s12, s6);
+    if (PIPE) {
+        if (fast) nl_walk_pipe<false>(nb, a.stride, cnt, pos, xi, yi, zi, L, invL, rc2, fx, fy, fz, s12, s6);
+        else nl_walk_pipe<true>(nb, a.stride, cnt, pos, xi, yi, zi, L, invL, rc2, fx, fy, fz, s12, s6);
+    } else {
+        if (fast) nl_walk<false, TPA>(nb, a.stride, cnt, sub, pos, xi, yi, zi, L, invL, rc2, fx, fy, fz, s12, s6);
+        else nl_walk<true, TPA>(nb, a.stride, cnt, sub, pos, xi, yi, zi, L, invL, rc2, fx, fy, fz, s12, s6);
+    }
     if (TPA > 1) { // force partials of the TPA lanes of an atom, fixed butterfly order
 #pragma unroll
         for (int o = 1; o < TPA; o <<= 1) {
@@ -1013,6 +1061,8 @@ int nlist_plan(ljmd_ctx *c)
     // lanes per atom of the step kernel: 4 is opt-in (LJMD_NL_TPA=4): measured no gain at N=32k on one GPU
     // (30.0 vs 28.0 us); meant for the small slabs of 8-GPU runs, not yet measured there
     w.tpa = 1;
+    w.pipe = (n <= 262144) ? 1 : 0; // software-pipelined gathers for small systems (few warps per SM)
+    if (const char *e = getenv("LJMD_NL_PIPE")) w.pipe = atoi(e) != 0;
     if (const char *e = getenv("LJMD_NL_TPA")) w.tpa = (atoi(e) == 4) ? 4 : 1;
     w.narr = c->st.rux ? 15 : 12;
     // work units: runs of about NL_BS atoms along z inside one cell column
@@ -1149,7 +1199,11 @@ int nlist_enqueue_step_kernel(ljmd_ctx *c)
     const int tpa = c->nw.tpa;
     const int grid = c->nw.sh_on ? c->nw.own_blocks : (c->sc.n + NL_BS / tpa - 1) / (NL_BS / tpa);
 #define LJMD_NL_LAUNCH(TR, SHD, T) nl_step_kernel<1, TR, SHD, T><<<grid, NL_BS, 0, c->stream>>>(a)
-    if (c->nw.sh_on) {
+#define LJMD_NL_LAUNCH_PIPE(TR, SHD) nl_step_kernel<1, TR, SHD, 1, true><<<grid, NL_BS, 0, c->stream>>>(a)
+    if (c->nw.pipe && tpa == 1) { // small systems / small slabs: pipelined gathers
+        if (c->nw.sh_on) { if (track) LJMD_NL_LAUNCH_PIPE(true, true); else LJMD_NL_LAUNCH_PIPE(false, true); }
+        else { if (track) LJMD_NL_LAUNCH_PIPE(true, false); else LJMD_NL_LAUNCH_PIPE(false, false); }
+    } else if (c->nw.sh_on) {
         if (tpa == 4) { if (track) LJMD_NL_LAUNCH(true, true, 4); else LJMD_NL_LAUNCH(false, true, 4); }
         else { if (track) LJMD_NL_LAUNCH(true, true, 1); else LJMD_NL_LAUNCH(false, true, 1); }
     } else {
@@ -1157,6 +1211,7 @@ int nlist_enqueue_step_kernel(ljmd_ctx *c)
         else { if (track) LJMD_NL_LAUNCH(true, false, 1); else LJMD_NL_LAUNCH(false, false, 1); }
     }
 #undef LJMD_NL_LAUNCH
+#undef LJMD_NL_LAUNCH_PIPE
     if (!c->capturing) c->launches++;
     LJMD_CUDA_CHECK(cudaGetLastError());
     c->nw.cur_host ^= 1;
@@ -1406,6 +1461,8 @@ extern "C" int ljmd_ctx_slab_attach(ljmd_ctx *c, int32_t rank, int32_t world, co
         slab_layers(w.nc, rank, world, &w.xlo, &w.xhi);
         // CTAs of the step kernel: room for 30 % more atoms than the mean slab (+ one layer's worth)
         const double mean = (double)c->sc.n * (w.xhi - w.xlo) / w.nc;
+        w.pipe = (mean <= 262144.0) ? 1 : 0;
+        if (const char *e = getenv("LJMD_NL_PIPE")) w.pipe = atoi(e) != 0;
         const int apb = NL_BS / w.tpa;
         w.own_blocks = (int)((1.3 * mean + 4096.0) / apb) + 1;
         if (w.own_blocks > w.nblk * w.tpa) w.own_blocks = w.nblk * w.tpa;

@@ -149,6 +149,7 @@ struct NlistWork {
     size_t stride;       // slots per entry group (n rounded up to 32); see nl_entry() in lj_nlist.cu
     int nblk, narr;
     int tpa;             // lanes per atom of the step kernel (1 or 4)
+    int pipe;            // software-pipelined gathers (small systems)
     int cur_host;        // host mirror of NlCtl::cur
     long long rebuilds_host, rebuilds_counted;
     int *cell_of_slot, *cell_count, *cell_start, *cell_cursor, *tile_sum;
