@@ -112,6 +112,10 @@ def load_library() -> C.CDLL:
         L.ljmd_ctx_destroy.argtypes = [C.c_void_p]
         L.ljmd_params_init.argtypes = [C.POINTER(SimParams), C.c_int32, C.c_double, C.c_double,
                                        C.c_double, C.c_int32]
+        # the drop-in pair takes raw addresses (cached per SimState): the ctypes conversions of nine
+        # numpy arrays used to cost ~30 us per call, a third of the whole host-array call at N=4000
+        L.ljmd_compute_lj.argtypes = [C.POINTER(SimParams)] + [C.c_void_p] * 6 + [_DP] * 3
+        L.ljmd_verlet_step.argtypes = [C.POINTER(SimParams)] + [C.c_void_p] * 9 + [_DP] * 4
         _lib = L
     return _lib
 
@@ -157,6 +161,20 @@ class SimState:
     def arrays(self):
         return [getattr(self, k) for k in self.NAMES]
 
+    def _addresses(self):
+        """Device-call addresses of the nine arrays, validated once and cached until an array
+        object is replaced (the drop-in calls update the arrays in place, like the reference)."""
+        arrs = (self.rx, self.ry, self.rz, self.vx, self.vy, self.vz, self.ax, self.ay, self.az)
+        cache = self.__dict__.get("_addr_cache")
+        if cache is not None and all(a is b for a, b in zip(arrs, cache[0])):
+            return cache[1]
+        for a in arrs:
+            if a.dtype != np.float64 or not a.flags.c_contiguous:
+                raise TypeError("state arrays must be C-contiguous float64")
+        addrs = tuple(a.ctypes.data for a in arrs)
+        self.__dict__["_addr_cache"] = (arrs, addrs)
+        return addrs
+
     def copy(self) -> "SimState":
         s = SimState.__new__(SimState)
         for k in self.NAMES:
@@ -184,9 +202,8 @@ def compute_lj_potential_energy(params: SimParams, state: SimState):
     """physics/lj_potential_energy.f90:46.  Overwrites state.ax/ay/az; returns
     (epot, d_epot, dd_epot)."""
     e, d, dd = C.c_double(), C.c_double(), C.c_double()
-    _chk(load_library().ljmd_compute_lj(C.byref(params), _p(state.rx), _p(state.ry), _p(state.rz),
-                                        _p(state.ax), _p(state.ay), _p(state.az), C.byref(e),
-                                        C.byref(d), C.byref(dd)))
+    ad = state._addresses()
+    _chk(load_library().ljmd_compute_lj(params, ad[0], ad[1], ad[2], ad[6], ad[7], ad[8], e, d, dd))
     return e.value, d.value, dd.value
 
 
@@ -194,8 +211,7 @@ def verlet_step(params: SimParams, state: SimState):
     """physics/verlet.f90:41.  Updates all nine arrays in place; returns
     (epot, ekin, d_epot, dd_epot)."""
     e, k, d, dd = C.c_double(), C.c_double(), C.c_double(), C.c_double()
-    _chk(load_library().ljmd_verlet_step(C.byref(params), *[_p(a) for a in state.arrays()],
-                                         C.byref(e), C.byref(k), C.byref(d), C.byref(dd)))
+    _chk(load_library().ljmd_verlet_step(params, *state._addresses(), e, k, d, dd))
     return e.value, k.value, d.value, dd.value
 
 
