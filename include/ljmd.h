@@ -224,6 +224,9 @@ int ljmd_ctx_slab_rebuild(ljmd_ctx *ctx, int32_t force);
 int ljmd_ctx_slab_run(ljmd_ctx *ctx, int32_t max_steps, int32_t *steps_done, int32_t *halted,
                       double *obs4);
 
+/* Self-check of the neighbour-list path: total momentum (sum of v) of the atoms handled by the last
+ * step launch -- an invariant of the dynamics (a sharded run adds the ranks' shares). */
+int ljmd_ctx_nlist_momentum(ljmd_ctx *ctx, double *p3);
 /* Publishes the flag of the last completed step now (normally done by the first CTA of the next
  * step kernel); needed only when ranks are emulated by alternately stepped contexts of ONE process. */
 int ljmd_ctx_slab_publish(ljmd_ctx *ctx);

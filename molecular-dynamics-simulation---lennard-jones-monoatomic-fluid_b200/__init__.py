@@ -91,6 +91,7 @@ ABI_SYMBOLS = [
     "ljmd_ctx_slab_export", "ljmd_ctx_slab_attach", "ljmd_ctx_slab_bounds", "ljmd_ctx_slab_pack",
     "ljmd_ctx_slab_unpack", "ljmd_ctx_slab_drift", "ljmd_ctx_slab_rebuild", "ljmd_ctx_slab_run",
     "ljmd_ctx_debug_checksum", "ljmd_ctx_series_arm", "ljmd_ctx_series_fetch", "ljmd_ctx_slab_publish",
+    "ljmd_ctx_nlist_momentum",
 ]
 MAX_RANKS = 8
 
@@ -329,6 +330,12 @@ class Context:
         ser = np.zeros((nsteps, self.nreplicas, 4))
         _chk(self._L.ljmd_ctx_series_fetch(self._h, int(nsteps), _p(ser)))
         return ser[:, 0, :] if self.nreplicas == 1 else ser
+
+    def nlist_momentum(self) -> np.ndarray:
+        """Sum of v over the atoms the last step launch handled (self-check: conserved)."""
+        p3 = np.zeros(3)
+        _chk(self._L.ljmd_ctx_nlist_momentum(self._h, _p(p3)))
+        return p3
 
     def slab_publish(self) -> None:
         _chk(self._L.ljmd_ctx_slab_publish(self._h))

@@ -84,6 +84,7 @@ struct NlArgs {
     double *spart; // [nblk][5]
     int nblk;
     double *obs;   // [4]
+    double *mom;   // [3] total momentum of the atoms handled by the last step launch
     // ---- slab sharding over GPUs (sh_on): this rank owns the cell layers cx in [xlo, xhi)
     int sh_on, rank, world, xlo, xhi;
     double4 *peer_p4[LJMD_MAX_RANKS]; // p4 base ([2][n]) of every rank, mapped into this process
@@ -483,6 +484,7 @@ __device__ __forceinline__ void nl_pair(double xi, double yi, double zi, const d
 // Walk of one atom's list.  The index groups stream from HBM (read once: cache-streaming loads, a
 // ring of NL_PF groups is kept in flight); the packed positions are gathered from L1/L2.
 constexpr int NL_PF = 3;
+constexpr int NL_NS = 8; // per-CTA partial sums: S12, S6, sum vx^2, vy^2, vz^2, sum vx, vy, vz
 
 // TPA lanes share one atom: lane `sub` takes the entry groups sub, sub+TPA, ... (TPA = 4 gives small
 // systems -- and the slabs of a sharded run -- four times as many threads; the lane partials are
@@ -626,7 +628,7 @@ template <int MODE, bool TRACK, bool SH, int TPA, bool PIPE = false>
 __global__ void __launch_bounds__(NL_BS, PIPE ? 512 / NL_BS : TPA > 1 ? 640 / NL_BS : (SH || MODE == 0) ? 768 / NL_BS : 1024 / NL_BS)
 nl_step_kernel(NlArgs a)
 {
-    __shared__ double scratch[5 * (NL_BS / 32)];
+    __shared__ double scratch[NL_NS * (NL_BS / 32)];
     __shared__ bool is_last;
     __shared__ int s_viol;
     constexpr int APB = NL_BS / TPA; // atoms per CTA
@@ -701,7 +703,7 @@ nl_step_kernel(NlArgs a)
         }
     }
 
-    double s[5] = {s12, s6, 0.0, 0.0, 0.0}; // every lane contributes its own share of the pair sums
+    double s[NL_NS] = {s12, s6, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}; // every lane contributes its own share of the pair sums
     double d2 = 0.0;
     if (valid && sub == 0) {
         const size_t ix = i, iy = ix + n, iz = iy + n;
@@ -742,17 +744,18 @@ nl_step_kernel(NlArgs a)
         }
         a.a[ix] = axn; a.a[iy] = ayn; a.a[iz] = azn;
         s[2] = vx * vx; s[3] = vy * vy; s[4] = vz * vz; // verlet.f90:93-95
+        s[5] = vx; s[6] = vy; s[7] = vz;                // total momentum: an invariant (Newton 3), kept as a self-check
     }
-    block_sum<5>(s, scratch);
+    block_sum<NL_NS>(s, scratch);
     if (MODE == 1) nl_block_max(d2, scratch, a.ctl);
     if (SH) { // EVERY thread's remote halo stores are performed system-wide before thread 0 takes the ticket
         __threadfence_system();
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        double *sp = a.spart + (size_t)blockIdx.x * 5;
+        double *sp = a.spart + (size_t)blockIdx.x * NL_NS;
 #pragma unroll
-        for (int q = 0; q < 5; ++q) sp[q] = s[q];
+        for (int q = 0; q < NL_NS; ++q) sp[q] = s[q];
         __threadfence();
         const unsigned t = atomicAdd(&a.ctl->ticket_step, 1u);
         is_last = (t == (unsigned)nact - 1);
@@ -762,13 +765,14 @@ nl_step_kernel(NlArgs a)
     __threadfence();
 
     // fixed-order reduction of all CTA partials
-    double r[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    double r[NL_NS] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (int b = threadIdx.x; b < (SH ? nact : (int)gridDim.x); b += NL_BS) {
 #pragma unroll
-        for (int q = 0; q < 5; ++q) r[q] += __ldcg(a.spart + (size_t)b * 5 + q);
+        for (int q = 0; q < NL_NS; ++q) r[q] += __ldcg(a.spart + (size_t)b * NL_NS + q);
     }
-    block_sum<5>(r, scratch);
+    block_sum<NL_NS>(r, scratch);
     if (threadIdx.x == 0) {
+        a.mom[0] = r[5]; a.mom[1] = r[6]; a.mom[2] = r[7]; // sum of v over the atoms this launch handled
         // ordered pairs: every unordered pair was counted twice
         const double S12 = 0.5 * r[0], S6 = 0.5 * r[1];
         double o[4];
@@ -1027,6 +1031,7 @@ static NlArgs make_args(ljmd_ctx *c, int eval_sel)
     a.ctl = w.ctl; a.sctl = c->fw.ctl;
     a.spart = w.spart; a.nblk = w.nblk;
     a.obs = c->fw.obs;
+    a.mom = w.mom;
     a.eval_sel = eval_sel;
     a.pair_counts = nullptr;
     a.sh_on = w.sh_on; a.rank = w.rank; a.world = w.world; a.xlo = w.xlo; a.xhi = w.xhi;
@@ -1097,7 +1102,9 @@ int nlist_plan(ljmd_ctx *c)
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.p4, 0, sizeof(double4) * 2 * (size_t)n, c->stream));
     LJMD_CUDA_CHECK(cudaMalloc(&w.r0, sizeof(double) * 3 * (size_t)n));
     LJMD_CUDA_CHECK(cudaMalloc(&w.alt, sizeof(double) * 15 * (size_t)n));
-    LJMD_CUDA_CHECK(cudaMalloc(&w.spart, sizeof(double) * 5 * 4 * (size_t)w.nblk)); // room for 4 lanes per atom
+    LJMD_CUDA_CHECK(cudaMalloc(&w.spart, sizeof(double) * NL_NS * 4 * (size_t)w.nblk)); // room for 4 lanes per atom
+    LJMD_CUDA_CHECK(cudaMalloc(&w.mom, sizeof(double) * 4));
+    LJMD_CUDA_CHECK(cudaMemsetAsync(w.mom, 0, sizeof(double) * 4, c->stream));
     LJMD_CUDA_CHECK(cudaMalloc(&w.ctl, sizeof(NlCtl)));
     LJMD_CUDA_CHECK(cudaMalloc(&w.flags, sizeof(int) * 2 * LJMD_MAX_RANKS));
     if (getenv("LJMD_SLAB_DEBUG")) {
@@ -1111,7 +1118,7 @@ int nlist_plan(ljmd_ctx *c)
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.nb_cnt, 0, sizeof(int) * (size_t)n, c->stream));
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.interior, 0, (size_t)n, c->stream));
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.r0, 0, sizeof(double) * 3 * (size_t)n, c->stream));
-    LJMD_CUDA_CHECK(cudaMemsetAsync(w.spart, 0, sizeof(double) * 5 * 4 * (size_t)w.nblk, c->stream));
+    LJMD_CUDA_CHECK(cudaMemsetAsync(w.spart, 0, sizeof(double) * NL_NS * 4 * (size_t)w.nblk, c->stream));
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.ctl, 0, sizeof(NlCtl), c->stream));
     nl_identity_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, w.orig, w.slot_of_orig);
     LJMD_CUDA_CHECK(cudaGetLastError());
@@ -1124,7 +1131,7 @@ void nlist_free(ljmd_ctx *c)
     NlistWork &w = c->nw;
     cudaFree(w.cell_of_slot); cudaFree(w.cell_count); cudaFree(w.cell_start); cudaFree(w.cell_cursor); cudaFree(w.tile_sum);
     cudaFree(w.keys); cudaFree(w.orig); cudaFree(w.orig_alt); cudaFree(w.slot_of_orig); cudaFree(w.interior);
-    cudaFree(w.nb_cnt); cudaFree(w.nbr); cudaFree(w.p4); cudaFree(w.r0); cudaFree(w.alt); cudaFree(w.spart); cudaFree(w.ctl);
+    cudaFree(w.nb_cnt); cudaFree(w.nbr); cudaFree(w.p4); cudaFree(w.r0); cudaFree(w.alt); cudaFree(w.spart); cudaFree(w.mom); cudaFree(w.ctl);
     for (int q = 0; q < LJMD_MAX_RANKS; ++q) {
         if (w.ipc_p4[q]) cudaIpcCloseMemHandle(w.ipc_p4[q]);
         if (w.ipc_flags[q]) cudaIpcCloseMemHandle(w.ipc_flags[q]);
@@ -1581,6 +1588,23 @@ extern "C" int ljmd_ctx_slab_rebuild(ljmd_ctx *c, int32_t force)
     if (rc == LJMD_OK) rc = nlist_check_overflow(c);
     if (prev != c->device) cudaSetDevice(prev);
     return rc;
+}
+
+// Total momentum (sum of v over the atoms the last step / force launch of this context handled).
+// Newton's third law makes it an invariant of the dynamics; a sharded run sums the ranks' shares.
+extern "C" int ljmd_ctx_nlist_momentum(ljmd_ctx *c, double *p3)
+{
+    clear_error();
+    if (!c || !p3) return set_error(LJMD_ERR_NULL, "ljmd_ctx_nlist_momentum(): NULL argument.");
+    if (c->method != LJMD_METHOD_NLIST) return set_error(LJMD_ERR_ARG, "ljmd_ctx_nlist_momentum(): neighbour-list method only.");
+    int prev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
+    cudaError_t e = cudaMemcpyAsync(p3, c->nw.mom, sizeof(double) * 3, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (prev != c->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return set_error(LJMD_ERR_CUDA, "ljmd_ctx_nlist_momentum(): %s", cudaGetErrorString(e));
+    return LJMD_OK;
 }
 
 extern "C" int ljmd_ctx_slab_publish(ljmd_ctx *c)

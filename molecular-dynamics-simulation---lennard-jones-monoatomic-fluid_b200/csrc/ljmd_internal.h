@@ -161,6 +161,7 @@ struct NlistWork {
     int nzg, nunits, cap_stage;
     size_t smem_bytes;
     double *r0, *alt, *spart;
+    double *mom;         // [3] momentum of the atoms handled by the last step launch
     double4 *p4;         // [2][n] packed positions (x, y, z, 0) of the two position buffers
     NlCtl *ctl;
     cudaStream_t side_stream; // captures the IF-node bodies of the step graph

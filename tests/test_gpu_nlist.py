@@ -153,15 +153,17 @@ def test_nlist_multistep_rebuilds_graph_and_determinism(lj, O):
                 ctx.upload(_state(lj, st))
                 ctx.compute_forces()
                 obs = ctx.step(nsteps)
+                mom = float(np.abs(ctx.nlist_momentum()).max())
                 d = ctx.download()
                 info = ctx.nlist_info()
-        return obs.copy(), [a.copy() for a in d.arrays()], info
+        return obs.copy(), [a.copy() for a in d.arrays()], info, mom
 
     a = run()
     b = run()
     c = run(LJMD_NL_NOGRAPH=1)
     assert a[2]["rebuilds"] >= 3, a[2]
     assert a[2]["rebuilds"] == c[2]["rebuilds"]
+    assert a[3] < 1e-8  # total momentum stays zero (Newton 3 + symmetric ordered pairs): built-in self-check
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[0], c[0])
     for x, y, z in zip(a[1], b[1], c[1]):
         assert np.array_equal(x, y) and np.array_equal(x, z)
@@ -322,6 +324,8 @@ def test_nlist_slab_two_ranks_emulated(lj, O):
                 if res[0][0] == 1:
                     done_total += 1
                     obs = res[0][2] + res[1][2]
+                    # the ranks' momentum shares add up to zero at every step
+                    assert np.abs(ctxs[0].nlist_momentum() + ctxs[1].nlist_momentum()).max() < 1e-8
                 if res[0][1]:
                     gather()
                     for c in ctxs:
