@@ -96,6 +96,38 @@ def test_cfg1_anchors(O):
     assert abs(o10[0] + o10[1] - (-554.516553827825)) < 1e-7
 
 
+def _fcc_shell_sums(a, rc):
+    """Independent known answer for a perfect FCC crystal: sums over the lattice vectors
+    R = (a/2)(i,j,k), i+j+k even, 0 < |R| < rc, of R^-12 and R^-6, plus the neighbour count.  No pair
+    loop and no minimum image: valid while rc < L/2 so every neighbour is a distinct image."""
+    m = int(np.ceil(2.0 * rc / a)) + 1
+    g = np.arange(-m, m + 1)
+    i, j, k = np.meshgrid(g, g, g, indexing="ij")
+    keep = ((i + j + k) % 2 == 0) & ((i != 0) | (j != 0) | (k != 0))
+    r2 = (0.5 * a) ** 2 * (i[keep] ** 2 + j[keep] ** 2 + k[keep] ** 2).astype(np.float64)
+    r2 = np.sort(r2[r2 < rc * rc])[::-1]  # small terms first
+    return float(np.sum(r2 ** -6.0)), float(np.sum(r2 ** -3.0)), int(r2.size)
+
+
+def test_fcc_lattice_sum_known_answer(O):
+    # the enumerator itself against the literature FCC lattice sums (in nearest-neighbour units):
+    # A12 = 12.131880196..., A6 = 14.453920885... (Kittel; converged to 1e-9 / 3e-3 at rc = 12 d)
+    s12, s6, _ = _fcc_shell_sums(np.sqrt(2.0), 12.0)
+    assert abs(s12 - 12.131880196) < 1e-8
+    assert 0.0 < 14.453920885 - s6 < 4.0 * np.pi * np.sqrt(2.0) / (3.0 * 12.0 ** 3) * 1.01  # missing tail: integral bound
+    # cfg1 (k = 5, L = 10, rc = 4.9): U, r dU/dr and r^2 d2U/dr2 sums of lj_potential_energy.f90:132-193
+    p, st = make_config(O, "cfg1")
+    ax, ay, az, e, d, dd = O.compute_lj(p, *st[:3])
+    tu, td, tdd = O.tail_corrections(p)
+    s12, s6, nnb = _fcc_shell_sums(10.0 / 5.0, 4.9)
+    n = 500
+    assert nnb == 248 and O.count_pairs_in_cutoff(p, *st[:3]) == n * nnb // 2
+    half = 0.5 * n
+    assert rel_err(e, half * 4.0 * (s12 - s6) + tu) < 1e-12
+    assert rel_err(d, half * 24.0 * (s6 - 2.0 * s12) + td) < 1e-12
+    assert rel_err(dd, half * 24.0 * (26.0 * s12 - 7.0 * s6) + tdd) < 1e-12
+
+
 def test_newton3_and_momentum(O):
     p, st = make_config(O, "cfg1")
     s = melt(O, p, st, 200)
@@ -113,6 +145,25 @@ def test_energy_conservation_smooth_case(O):
     _, ser = O.run_steps(p, 300, s, want_series=True)
     etot = ser[:, 0] + ser[:, 1]
     assert np.ptp(etot) < 1e-2 * abs(etot[0])
+
+
+def test_velocity_verlet_is_time_reversible(O):
+    # verlet.f90:58-95 is the symmetric kick-drift-kick scheme: n steps, v -> -v, n steps returns to
+    # the start up to rounding (the wrap of geometry_pbc.f90 only shifts by multiples of L)
+    p, st = make_config(O, "small_cells")
+    s = melt(O, p, st, 100)
+    start = [a.copy() for a in s]
+    O.run_steps(p, 200, s)
+    assert max(np.abs(s[q] - start[q]).max() for q in range(3)) > 1e-2  # it did move
+    for q in (3, 4, 5):
+        s[q] *= -1.0
+    O.run_steps(p, 200, s)
+    L = 10.259855680060184
+    for q in range(3):
+        d = s[q] - start[q]
+        d -= L * np.rint(d / L)
+        assert np.abs(d).max() < 1e-9
+        assert np.abs(s[q + 3] + start[q + 3]).max() < 1e-9
 
 
 def test_golden_cfg1(O):
