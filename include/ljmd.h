@@ -277,6 +277,33 @@ int ljmd_bench_chunk_cycles(int32_t ri, int32_t rj, int32_t dense, int32_t warps
  * chains), in TFLOP/s; the roofline denominator for the all-pairs kernel. */
 int ljmd_measure_fp64_peak(int32_t device, double *tflops);
 
+/* ==========================================================================================
+ * Trajectory consumers: the heavy loops of the reference's analysis script
+ * scripts/md_one_run_analysis.py, on the arrays its read_rva (:345-397) returns -- row-major
+ * [n_snap][n] per component, HOST pointers (copied to the device inside the call).
+ * `device` < 0 = current device.  `kernel_ms` (may be NULL) receives the CUDA-event time of the kernel.
+ * ========================================================================================== */
+
+/* compute_rdf (:537-598), the pair loop :566-584: for every snapshot and every pair i < j,
+ * d = r_j - r_i, d -= L*rint(d/L), r = sqrt(dx*dx + dy*dy + dz*dz); pairs with r < rmax are counted in
+ * bin (int)(r/dr), dr = rmax/nbins.  hist[nbins] receives UNORDERED pair counts (the reference adds
+ * 2.0 per pair, :584) and is bit-exact.  The snapshot / particle subsampling (:555-561) and the
+ * normalisation (:586-597) are host work on <= nbins numbers (analysis.py).  Returns LJMD_ERR_ARG if a
+ * pair with r < rmax lands in bin index nbins (the reference raises IndexError there). */
+int ljmd_rdf_histogram(const double *rx, const double *ry, const double *rz, int32_t n_snap, int32_t n,
+                       double box_length, int32_t nbins, double rmax, int64_t *hist, int32_t device,
+                       double *kernel_ms);
+
+/* compute_msd_tau_timeorig (:404-441, kind = LJMD_CORR_MSD, arrays = unwrapped positions) and
+ * compute_vacf_tau_timeorig (:444-489, kind = LJMD_CORR_VACF, arrays = velocities): time-origin
+ * averaged over t0 = 0, stride, 2*stride, ... < n_snap-1 and over particles.  max_lag < 0 or
+ * > n_snap-1 means n_snap-1 (:420-422); origin_stride < 1 means 1 (:423).  out has
+ * min(max_lag, n_snap-1)+1 entries (1 entry when n_snap < 2, :416-417 / :456-458). */
+enum { LJMD_CORR_MSD = 0, LJMD_CORR_VACF = 1 };
+int ljmd_time_correlation(const double *ax, const double *ay, const double *az, int32_t n_snap, int32_t n,
+                          int32_t max_lag, int32_t origin_stride, int32_t kind, double *out, int32_t device,
+                          double *kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

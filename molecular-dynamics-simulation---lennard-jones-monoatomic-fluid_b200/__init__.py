@@ -91,7 +91,7 @@ ABI_SYMBOLS = [
     "ljmd_ctx_slab_export", "ljmd_ctx_slab_attach", "ljmd_ctx_slab_bounds", "ljmd_ctx_slab_pack",
     "ljmd_ctx_slab_unpack", "ljmd_ctx_slab_drift", "ljmd_ctx_slab_rebuild", "ljmd_ctx_slab_run",
     "ljmd_ctx_debug_checksum", "ljmd_ctx_series_arm", "ljmd_ctx_series_fetch", "ljmd_ctx_slab_publish",
-    "ljmd_ctx_nlist_momentum",
+    "ljmd_ctx_nlist_momentum", "ljmd_rdf_histogram", "ljmd_time_correlation",
 ]
 MAX_RANKS = 8
 
