@@ -79,7 +79,34 @@ class RandomUniform:
         return mj * FAC
 
     def draw(self, count: int) -> np.ndarray:
-        return np.array([self() for _ in range(count)], dtype=np.float64)
+        """`count` successive values.  The recurrence x[k] = (x[k-55] - x[k-24]) mod MBIG only looks
+        24 or more values back, so it is evaluated 24 values at a time with numpy (3 N draws for
+        N = 2^20 would otherwise be a 3-million-iteration Python loop); short requests and the
+        table initialisation use the scalar path.  Bit-identical to calling the object `count` times."""
+        count = int(count)
+        if count < 256:
+            return np.array([self() for _ in range(count)], dtype=np.float64)
+        first = self()                                   # initialises the table if needed
+        # history in generation order: value generated i calls ago sits at hist[-i]
+        order = [(self.inext - 1 - i) % 55 + 1 for i in range(55)]   # newest ... oldest slot (1-based)
+        hist = np.empty(55 + count - 1, dtype=np.float64)
+        hist[:55] = [self.ma[j] for j in reversed(order)]
+        for k in range(55, 55 + count - 1, 24):
+            m = min(24, 55 + count - 1 - k)
+            v = hist[k - 55:k - 55 + m] - hist[k - 24:k - 24 + m]
+            v[v < 0.0] += MBIG
+            hist[k:k + m] = v
+        out = np.empty(count, dtype=np.float64)
+        out[0] = first
+        out[1:] = hist[55:] * FAC
+        # write the last 55 values back into the circular table and advance the cursors
+        adv = count - 1
+        tail = hist[-55:]
+        self.inext = (self.inext - 1 + adv) % 55 + 1
+        self.inextp = (self.inextp - 1 + adv) % 55 + 1
+        for i in range(55):                              # value generated i calls ago -> slot inext - i
+            self.ma[(self.inext - 1 - i) % 55 + 1] = float(tail[54 - i])
+        return out
 
 
 def _seqsum(x: np.ndarray) -> float:
@@ -174,14 +201,36 @@ def _write_record(f, payload: bytes) -> None:
     f.write(struct.pack("<i", len(payload)))
 
 
-def _read_record(f) -> bytes:
-    head = f.read(4)
-    if len(head) != 4:
+def _marker_size(f) -> int:
+    """4-byte record markers (gfortran default) or 8-byte ones (-frecord-marker=8), detected like
+    the reference's reader does (md_one_run_analysis.py:262-291): the leading length must be
+    plausible and repeated after the payload."""
+    pos = f.tell()
+    head = f.read(64)
+    f.seek(pos)
+    for size, code in ((4, "<i"), (8, "<q")):
+        if len(head) >= 2 * size:
+            (nb,) = struct.unpack(code, head[:size])
+            if 0 < nb < 1_000_000_000:
+                f.seek(pos + size + nb)
+                tail = f.read(size)
+                f.seek(pos)
+                if len(tail) == size and struct.unpack(code, tail)[0] == nb:
+                    return size
+    return 4
+
+
+def _read_record(f, marker: int = 4) -> bytes:
+    code = "<i" if marker == 4 else "<q"
+    head = f.read(marker)
+    if len(head) != marker:
         raise EOFError("unformatted record: missing length marker")
-    (nb,) = struct.unpack("<i", head)
+    (nb,) = struct.unpack(code, head)
+    if nb < 0:
+        raise ValueError("unformatted record: negative length")
     payload = f.read(nb)
-    (nb2,) = struct.unpack("<i", f.read(4))
-    if nb2 != nb or len(payload) != nb:
+    tail = f.read(marker)
+    if len(payload) != nb or len(tail) != marker or struct.unpack(code, tail)[0] != nb:
         raise ValueError("unformatted record: length markers do not match")
     return payload
 
@@ -200,8 +249,9 @@ def write_rv_init(filename: str, state) -> None:
 def read_rv_init(filename: str, n: int):
     """md_simulation_program.f90:573-588.  Returns (rx, ry, rz, vx, vy, vz)."""
     with open(filename, "rb") as f:
-        r = np.frombuffer(_read_record(f), dtype="<f8")
-        v = np.frombuffer(_read_record(f), dtype="<f8")
+        ms = _marker_size(f)
+        r = np.frombuffer(_read_record(f, ms), dtype="<f8")
+        v = np.frombuffer(_read_record(f, ms), dtype="<f8")
     if len(r) != 3 * n or len(v) != 3 * n:
         raise ValueError("read_rv_init(): record length does not match params%n")
     return tuple(np.ascontiguousarray(x) for x in (r[:n], r[n:2 * n], r[2 * n:], v[:n], v[n:2 * n], v[2 * n:]))
@@ -236,11 +286,12 @@ class RvaWriter:
 def read_rva(filename: str):
     """Reads what RvaWriter / the reference writes: (header dict, list of (r, ru, v, a) arrays [3][n])."""
     with open(filename, "rb") as f:
-        n, L, dt, interval, nsnap = struct.unpack("<iddii", _read_record(f))
+        ms = _marker_size(f)
+        n, L, dt, interval, nsnap = struct.unpack("<iddii", _read_record(f, ms))
         samples = []
         while True:
             try:
-                recs = [np.frombuffer(_read_record(f), dtype="<f8").reshape(3, n) for _ in range(4)]
+                recs = [np.frombuffer(_read_record(f, ms), dtype="<f8").reshape(3, n) for _ in range(4)]
             except EOFError:
                 break
             samples.append(tuple(recs))

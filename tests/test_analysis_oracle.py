@@ -179,10 +179,11 @@ def test_rva_writer_is_read_by_the_independent_reader(A, lj, O, tmp_path):
     p8.write_bytes(bytes(out))
     d8 = A.read_rva(p8)
     assert np.array_equal(d8["vx"], d["vx"]) and d8["n_snapshots"] == 3
-    # package reader agrees with the oracle reader
-    hdr, samples = ic.read_rva(str(path))
-    assert hdr["n"] == 500 and len(samples) == 3
-    assert np.array_equal(samples[2][0][0], d["rx"][2]) and np.array_equal(samples[1][2][1], d["vy"][1])
+    # package reader agrees with the oracle reader, for both marker sizes
+    for f in (path, p8):
+        hdr, samples = ic.read_rva(str(f))
+        assert hdr["n"] == 500 and hdr["n_snapshots"] == 3 and len(samples) == 3
+        assert np.array_equal(samples[2][0][0], d["rx"][2]) and np.array_equal(samples[1][2][1], d["vy"][1])
 
 
 def test_product_analysis_fails_loudly_without_gpu(lj, an):

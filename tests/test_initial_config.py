@@ -85,3 +85,14 @@ def test_rv_init_and_rva_files(ic, tmp_path):
     hdr, samples = ic.read_rva(g)
     assert hdr == {"n": n, "box_length": 10.0, "dt": 1e-4, "output_interval": 100, "n_snapshots": 2}
     assert len(samples) == 2 and np.array_equal(samples[1][1][2], ru[2]) and np.array_equal(samples[0][3][0], s.ax)
+
+
+def test_rng_block_draw_is_bit_identical_to_scalar_calls(ic):
+    # draw() evaluates the lagged recurrence 24 values at a time; values AND the state left behind
+    # must equal `count` scalar calls (base/random_numbers.f90:93-116)
+    for seed in (-12345, -7):
+        a, b = ic.RandomUniform(seed), ic.RandomUniform(seed)
+        want = np.array([a() for _ in range(3000)])
+        got = np.concatenate([b.draw(k) for k in (10, 300, 1, 1500, 255, 256, 678)])
+        assert np.array_equal(want, got)
+        assert [a() for _ in range(120)] == [b() for _ in range(120)]
