@@ -624,8 +624,20 @@ __device__ __forceinline__ void nl_st_release_sys(int *p, int v)
 // Single-GPU variants: <= 64 registers (32 warps per SM hide the gather latency).  The sharded
 // variants need a few more registers; they get up to 85 rather than being squeezed into 64 with
 // local-memory spills.
+// Resident threads per SM the register allocation is sized for (build-time knobs for A/B libraries,
+// `make variant`): PIPE 512, TPA > 1 640, sharded / force-only 768, plain step 1024.
+#ifndef LJMD_NL_THREADS_SH
+#define LJMD_NL_THREADS_SH 768
+#endif
+#ifndef LJMD_NL_THREADS_STEP
+#define LJMD_NL_THREADS_STEP 1024
+#endif
+#ifndef LJMD_NL_THREADS_PIPE
+#define LJMD_NL_THREADS_PIPE 512
+#endif
 template <int MODE, bool TRACK, bool SH, int TPA, bool PIPE = false>
-__global__ void __launch_bounds__(NL_BS, PIPE ? 512 / NL_BS : TPA > 1 ? 640 / NL_BS : (SH || MODE == 0) ? 768 / NL_BS : 1024 / NL_BS)
+__global__ void __launch_bounds__(NL_BS, PIPE ? LJMD_NL_THREADS_PIPE / NL_BS : TPA > 1 ? 640 / NL_BS
+                                         : (SH || MODE == 0) ? LJMD_NL_THREADS_SH / NL_BS : LJMD_NL_THREADS_STEP / NL_BS)
 nl_step_kernel(NlArgs a)
 {
     __shared__ double scratch[NL_NS * (NL_BS / 32)];
