@@ -77,6 +77,7 @@ static void refresh_constants(ljmd_ctx *c)
 static void drop_graphs(ljmd_ctx *c)
 {
     if (c->graph_chunk) { cudaGraphExecDestroy(c->graph_chunk); c->graph_chunk = nullptr; }
+    if (c->graph_compat) { cudaGraphExecDestroy(c->graph_compat); c->graph_compat = nullptr; }
 }
 
 struct DeviceGuard {
@@ -928,6 +929,40 @@ extern "C" int ljmd_verlet_step(const ljmd_params *params, double *rx, double *r
     const size_t nb = sizeof(double) * c->nR;
     double *arr[9] = {rx, ry, rz, vx, vy, vz, ax, ay, az};
     for (int k = 0; k < 9; ++k) memcpy(c->h_stage + (size_t)k * c->nR, arr[k], nb);
+    // Opt-in experiment (LJMD_COMPAT_GRAPH=1, not yet measured): upload, drift, force, finalize and
+    // download replayed as ONE graph launch instead of two copies and three kernel launches.
+    static const bool use_graph = getenv("LJMD_COMPAT_GRAPH") && atoi(getenv("LJMD_COMPAT_GRAPH")) != 0;
+    if (use_graph && c->method != LJMD_METHOD_NLIST) {
+        if (!c->graph_compat) {
+            cudaGraph_t g = nullptr;
+            LJMD_CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            c->capturing = true;
+            cudaError_t e = cudaMemcpyAsync(c->state_block, c->h_stage, 9 * nb, cudaMemcpyHostToDevice, c->stream);
+            int rc = (e == cudaSuccess) ? launch_drift(c, 0, 1) : LJMD_OK;
+            if (e == cudaSuccess && rc == LJMD_OK) rc = enqueue_step(c, 0, 2);
+            if (e == cudaSuccess && rc == LJMD_OK)
+                e = cudaMemcpyAsync(c->h_stage, c->state_block, 9 * nb + sizeof(double) * 4, cudaMemcpyDeviceToHost,
+                                    c->stream);
+            c->capturing = false;
+            const cudaError_t e2 = cudaStreamEndCapture(c->stream, &g);
+            if (rc != LJMD_OK || e != cudaSuccess || e2 != cudaSuccess) {
+                if (g) cudaGraphDestroy(g);
+                if (rc != LJMD_OK) return rc;
+                LJMD_CUDA_CHECK(e);
+                LJMD_CUDA_CHECK(e2);
+            }
+            const cudaError_t e3 = cudaGraphInstantiate(&c->graph_compat, g, 0);
+            cudaGraphDestroy(g);
+            LJMD_CUDA_CHECK(e3);
+        }
+        LJMD_CUDA_CHECK(cudaGraphLaunch(c->graph_compat, c->stream));
+        c->launches += 1 + kernels_per_step(c);
+        LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < 9; ++k) memcpy(arr[k], c->h_stage + (size_t)k * c->nR, nb);
+        const double *og = c->h_stage + 9 * c->nR;
+        *epot = og[0]; *ekin = og[1]; *d_epot = og[2]; *dd_epot = og[3];
+        return LJMD_OK;
+    }
     LJMD_CUDA_CHECK(cudaMemcpyAsync(c->state_block, c->h_stage, 9 * nb, cudaMemcpyHostToDevice, c->stream));
     if (c->method == LJMD_METHOD_NLIST) {
         LJMD_TRY(nlist_reset_identity(c));

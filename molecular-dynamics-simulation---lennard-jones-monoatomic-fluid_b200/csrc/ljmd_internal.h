@@ -204,6 +204,7 @@ struct ljmd_ctx {
     double *h_stage; // pinned staging for host<->device state copies (9*nR doubles)
     // graphs
     cudaGraphExec_t graph_chunk; // G steps
+    cudaGraphExec_t graph_compat; // opt-in: one ljmd_verlet_step host-array call (upload, step, download)
     int graph_chunk_steps;
     // series buffer
     double *d_series;
