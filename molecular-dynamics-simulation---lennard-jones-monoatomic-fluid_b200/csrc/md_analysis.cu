@@ -16,6 +16,7 @@
 // Layout: trajectories are [n_snap][n] row-major per component, like the arrays the reference's
 // read_rva returns (:355-390).
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "ljmd_internal.h"
 #include "reduce.cuh"
@@ -159,6 +160,94 @@ __global__ void __launch_bounds__(CORR_BS) time_corr_kernel(CorrArgs a)
     if (lane == 0) a.out[lag] = cnt > 0 ? __ddiv_rn(acc, (double)cnt) : 0.0; // :440-441
 }
 
+// ------------------------------------------------------------------------------------------
+// Opt-in second version (LJMD_CORR_TILED=1; written after the round's GPU budget was spent, never
+// run yet): register-tiled.  A warp owns CT_TO origins x CT_TL lags, lanes span the atoms, so a
+// row element is loaded once per warp for up to CT_TL (origin row) or several (target row,
+// stride 1: rows o + l coincide) of the 32 pairs instead of once per pair: ~4x less L1/L2
+// traffic than one warp per lag, and 32 independent accumulation chains per lane.
+// Each (origin, lag) mean is computed with exactly the arithmetic and order of corr_row_mean
+// and written to dmat[origin][lag]; time_corr_reduce_kernel then adds the origins in increasing
+// order per lag => results are bit-identical to time_corr_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int CT_TO = 4, CT_TL = 8; // per-warp tile: origins x lags
+constexpr int CT_WO = 2, CT_WL = 4; // warps of a CTA along origins / lags (8 warps)
+
+template <int KIND, bool STRIDE1>
+__global__ void __launch_bounds__(CORR_BS, 2) time_corr_tiled_kernel(CorrArgs a, double *dmat, int n_orig)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int o0 = (blockIdx.y * CT_WO + warp / CT_WL) * CT_TO; // first origin index of this warp
+    const int l0 = (blockIdx.x * CT_WL + warp % CT_WL) * CT_TL; // first lag of this warp
+    if (o0 >= n_orig || l0 > a.max_lag) return;                 // whole warp
+    const int stride = STRIDE1 ? 1 : a.stride;
+    const int last = a.n_snap - 1;
+    const size_t n = (size_t)a.n;
+    // Rows are clamped into the trajectory so that every load is in bounds; pairs that do not
+    // exist (origin index >= n_orig, lag beyond the origin's range) are dropped when storing.
+    const int base = o0 * stride + l0;
+    double acc[CT_TO][CT_TL];
+#pragma unroll
+    for (int o = 0; o < CT_TO; ++o)
+#pragma unroll
+        for (int l = 0; l < CT_TL; ++l) acc[o][l] = 0.0;
+
+    for (int p = lane; p < a.n; p += 32) {
+        double x0[CT_TO], y0[CT_TO], z0[CT_TO];
+#pragma unroll
+        for (int o = 0; o < CT_TO; ++o) {
+            const size_t r = (size_t)min((o0 + o) * stride, last) * n + p;
+            x0[o] = a.ax[r]; y0[o] = a.ay[r]; z0[o] = a.az[r];
+        }
+#pragma unroll
+        for (int o = 0; o < CT_TO; ++o) {
+#pragma unroll
+            for (int l = 0; l < CT_TL; ++l) {
+                // stride 1: the row depends on o + l only, so the unrolled loads of equal o + l merge
+                const int row = STRIDE1 ? min(base + (o + l), last) : min(base + o * stride + l, last);
+                const size_t r = (size_t)row * n + p;
+                const double x1 = a.ax[r], y1 = a.ay[r], z1 = a.az[r];
+                double t;
+                if (KIND == 0) {
+                    const double dx = __dsub_rn(x1, x0[o]), dy = __dsub_rn(y1, y0[o]), dz = __dsub_rn(z1, z0[o]);
+                    t = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                } else {
+                    t = __dadd_rn(__dadd_rn(__dmul_rn(x1, x0[o]), __dmul_rn(y1, y0[o])), __dmul_rn(z1, z0[o]));
+                }
+                acc[o][l] = __dadd_rn(acc[o][l], t);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < CT_TO; ++o) {
+        const int oi = o0 + o;
+        const int lmax = min(a.max_lag, last - oi * stride); // :429
+#pragma unroll
+        for (int l = 0; l < CT_TL; ++l) {
+            const double m = __ddiv_rn(warp_sum(acc[o][l]), (double)a.n);
+            if (lane == 0 && oi < n_orig && lmax > 0 && l0 + l <= lmax)
+                dmat[(size_t)oi * (a.max_lag + 1) + (l0 + l)] = m;
+        }
+    }
+}
+
+// out[lag] = mean over the origins that reach `lag`, added in increasing origin order (:437-441).
+__global__ void __launch_bounds__(CORR_BS) time_corr_reduce_kernel(CorrArgs a, const double *dmat, int n_orig)
+{
+    const int lag = blockIdx.x * CORR_BS + threadIdx.x;
+    if (lag > a.max_lag) return;
+    double acc = 0.0;
+    long long cnt = 0;
+    for (int o = 0; o < n_orig; ++o) {
+        const int lmax = min(a.max_lag, (a.n_snap - 1) - o * a.stride);
+        if (lmax <= 0) continue;
+        if (lag > lmax) break;
+        acc = __dadd_rn(acc, dmat[(size_t)o * (a.max_lag + 1) + lag]);
+        ++cnt;
+    }
+    a.out[lag] = cnt > 0 ? __ddiv_rn(acc, (double)cnt) : 0.0;
+}
+
 // Device buffers released on every return path.
 struct DevBuf {
     void *p = nullptr;
@@ -292,8 +381,29 @@ extern "C" int ljmd_time_correlation(const double *ax, const double *ay, const d
     LJMD_CUDA_CHECK(cudaEventCreate(&ev.e0));
     LJMD_CUDA_CHECK(cudaEventCreate(&ev.e1));
     LJMD_CUDA_CHECK(cudaEventRecord(ev.e0, 0));
-    if (kind == LJMD_CORR_MSD) time_corr_kernel<0><<<grid, CORR_BS>>>(a);
-    else time_corr_kernel<1><<<grid, CORR_BS>>>(a);
+    const char *tiled_env = getenv("LJMD_CORR_TILED");
+    const int n_orig = (n_snap - 1 + origin_stride - 1) / origin_stride; // len(range(0, n_snap-1, stride))
+    const size_t dmat_bytes = sizeof(double) * (size_t)n_orig * (size_t)(max_lag + 1);
+    DevBuf dmat;
+    if (tiled_env && atoi(tiled_env) != 0 && n_snap >= 2 && max_lag >= 1 && dmat_bytes <= ((size_t)2 << 30)) {
+        LJMD_CUDA_CHECK(cudaMalloc(&dmat.p, dmat_bytes));
+        const dim3 tgrid((unsigned)((max_lag + 1 + CT_WL * CT_TL - 1) / (CT_WL * CT_TL)),
+                         (unsigned)((n_orig + CT_WO * CT_TO - 1) / (CT_WO * CT_TO)));
+        if (tgrid.y > 65535u) return set_error(LJMD_ERR_UNSUPPORTED, "ljmd_time_correlation(): too many origins for the tiled kernel.");
+        double *dm = dmat.as<double>();
+        if (kind == LJMD_CORR_MSD) {
+            if (origin_stride == 1) time_corr_tiled_kernel<0, true><<<tgrid, CORR_BS>>>(a, dm, n_orig);
+            else time_corr_tiled_kernel<0, false><<<tgrid, CORR_BS>>>(a, dm, n_orig);
+        } else {
+            if (origin_stride == 1) time_corr_tiled_kernel<1, true><<<tgrid, CORR_BS>>>(a, dm, n_orig);
+            else time_corr_tiled_kernel<1, false><<<tgrid, CORR_BS>>>(a, dm, n_orig);
+        }
+        time_corr_reduce_kernel<<<(unsigned)((max_lag + CORR_BS) / CORR_BS), CORR_BS>>>(a, dm, n_orig);
+    } else if (kind == LJMD_CORR_MSD) {
+        time_corr_kernel<0><<<grid, CORR_BS>>>(a);
+    } else {
+        time_corr_kernel<1><<<grid, CORR_BS>>>(a);
+    }
     LJMD_CUDA_CHECK(cudaGetLastError());
     LJMD_CUDA_CHECK(cudaEventRecord(ev.e1, 0));
     LJMD_CUDA_CHECK(cudaDeviceSynchronize());
