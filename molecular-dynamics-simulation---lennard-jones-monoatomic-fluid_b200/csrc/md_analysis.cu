@@ -364,6 +364,7 @@ extern "C" int ljmd_time_correlation(const double *ax, const double *ay, const d
     if (max_lag < 0 || max_lag > n_snap - 1) max_lag = n_snap - 1;
     if (n_snap < 2) max_lag = 0;
     if (origin_stride < 1) origin_stride = 1;
+    if (origin_stride > n_snap) origin_stride = n_snap; // only t0 = 0 either way; keeps index products small
     AnalysisDevice dev;
     LJMD_TRY(dev.enter(device));
 
@@ -377,16 +378,17 @@ extern "C" int ljmd_time_correlation(const double *ax, const double *ay, const d
     a.out = dout.as<double>();
     const int lags_per_cta = CORR_BS / 32;
     const unsigned grid = (unsigned)((max_lag + 1 + lags_per_cta - 1) / lags_per_cta);
+    const char *tiled_env = getenv("LJMD_CORR_TILED");
+    const int n_orig = (n_snap - 1 + origin_stride - 1) / origin_stride; // len(range(0, n_snap-1, stride))
+    const size_t dmat_bytes = sizeof(double) * (size_t)n_orig * (size_t)(max_lag + 1);
+    const bool tiled = tiled_env && atoi(tiled_env) != 0 && n_snap >= 2 && max_lag >= 1 && dmat_bytes <= ((size_t)2 << 30);
+    DevBuf dmat;
+    if (tiled) LJMD_CUDA_CHECK(cudaMalloc(&dmat.p, dmat_bytes));
     EventPair ev;
     LJMD_CUDA_CHECK(cudaEventCreate(&ev.e0));
     LJMD_CUDA_CHECK(cudaEventCreate(&ev.e1));
     LJMD_CUDA_CHECK(cudaEventRecord(ev.e0, 0));
-    const char *tiled_env = getenv("LJMD_CORR_TILED");
-    const int n_orig = (n_snap - 1 + origin_stride - 1) / origin_stride; // len(range(0, n_snap-1, stride))
-    const size_t dmat_bytes = sizeof(double) * (size_t)n_orig * (size_t)(max_lag + 1);
-    DevBuf dmat;
-    if (tiled_env && atoi(tiled_env) != 0 && n_snap >= 2 && max_lag >= 1 && dmat_bytes <= ((size_t)2 << 30)) {
-        LJMD_CUDA_CHECK(cudaMalloc(&dmat.p, dmat_bytes));
+    if (tiled) {
         const dim3 tgrid((unsigned)((max_lag + 1 + CT_WL * CT_TL - 1) / (CT_WL * CT_TL)),
                          (unsigned)((n_orig + CT_WO * CT_TO - 1) / (CT_WO * CT_TO)));
         if (tgrid.y > 65535u) return set_error(LJMD_ERR_UNSUPPORTED, "ljmd_time_correlation(): too many origins for the tiled kernel.");
