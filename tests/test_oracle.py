@@ -128,6 +128,55 @@ def test_fcc_lattice_sum_known_answer(O):
     assert rel_err(dd, half * 24.0 * (26.0 * s12 - 7.0 * s6) + tdd) < 1e-12
 
 
+def test_virial_sums_are_the_scaling_derivatives_of_the_energy(O):
+    # Independent consistency of the three reductions (lj_potential_energy.f90:140,143,178 + tails
+    # :205-223): scaling positions, box and cutoff by lambda keeps every r/rc, so no pair crosses the
+    # cutoff and U(lambda) is smooth;  dU/dlambda = sum r dU/dr = d_epot and d2U/dlambda2 =
+    # sum r^2 d2U/dr2 = dd_epot at lambda = 1 (the tail terms scale like rho, rc and obey the same identity)
+    p, st = make_config(O, "cfg1")
+    s = melt(O, p, st, 300)
+    n, L, rc = 500, 10.0, 4.9
+    _, _, _, e0, d0, dd0 = O.compute_lj(p, *s[:3])
+
+    def energy(lam):
+        q = O.params_init(n, L * lam, 1e-4, rc * lam, 5)
+        return O.compute_lj(q, *[a * lam for a in s[:3]])[3]
+
+    h = 1e-3
+    em, ep, em2, ep2 = energy(1 - h), energy(1 + h), energy(1 - 2 * h), energy(1 + 2 * h)
+    d_fd = (8.0 * (ep - em) - (ep2 - em2)) / (12.0 * h)                          # 4th-order central differences
+    dd_fd = (-(ep2 + em2) + 16.0 * (ep + em) - 30.0 * e0) / (12.0 * h * h)
+    assert abs(d_fd - d0) < 1e-8 * abs(d0)
+    assert abs(dd_fd - dd0) < 1e-6 * abs(dd0)
+
+
+def test_accelerations_are_minus_the_energy_gradient(O):
+    # a_i = -dU/dr_i (unit mass; lj_potential_energy.f90:148-159,189-191), checked by central differences
+    # on atoms none of whose pairs lies within 1e-3 of the cutoff (the potential is truncated, not shifted)
+    p, st = make_config(O, "cfg1")
+    s = melt(O, p, st, 300)
+    x, y, z = [a.copy() for a in s[:3]]
+    ax, ay, az, *_ = O.compute_lj(p, x, y, z)
+    L, rc, h = 10.0, 4.9, 1e-5
+    checked = 0
+    for i in range(0, 500, 7):
+        d = np.stack([x - x[i], y - y[i], z - z[i]])
+        d -= L * np.rint(d / L)
+        r = np.sqrt((d * d).sum(axis=0))
+        if np.any(np.abs(r - rc) < 1e-3):
+            continue
+        for arr, acc in ((x, ax), (y, ay), (z, az)):
+            keep = arr[i]
+            arr[i] = keep + h
+            ep = O.compute_lj(p, x, y, z)[3]
+            arr[i] = keep - h
+            em = O.compute_lj(p, x, y, z)[3]
+            arr[i] = keep
+            assert abs(-(ep - em) / (2.0 * h) - acc[i]) < 1e-5 * max(1.0, abs(acc[i]))
+        checked += 1
+    assert checked >= 10
+
+
 def test_newton3_and_momentum(O):
     p, st = make_config(O, "cfg1")
     s = melt(O, p, st, 200)
