@@ -63,3 +63,29 @@ def test_means_guards_mirror_reference_stops(ob):
         acc.add_sample(np.array([[-1600.0, 0.0, 8000.0, -46000.0]]))   # ekin must be > 0
     with pytest.raises(ValueError):
         ob.thermodynamic_coefs_compute(1, 1000.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0)  # 3N-3 = 0
+
+
+def test_weak_constant_virial_known_answers(ob, O):
+    # Constant kinetic energy K and a constant, non-fluctuating dU = c, ddU = 0: every fluctuation term of
+    # thermodynamic_coefs.f90:118-203 cancels and the microcanonical formulas reduce to closed forms with
+    # f = 3N - 3:  Ca_v = f/2, gamma = 2N/f, K_S = N T (1 + gamma)/V - 2c/(9V), K_T = N T/V - 2c/(9V),
+    # and the two estimators alpha_E1, alpha_E2 coincide at -3f/(2c).  (c = 0, the ideal gas, makes both
+    # alpha_E denominators vanish and the reference stops there -- the guard is mirrored.)
+    n, V, K, c = 500, 1000.0, 750.0, 12.5
+    f = 3.0 * n - 3.0
+    T = 2.0 * K / f
+    P = (n / V) * T - c / (3.0 * V)          # md_means.f90:227 with W = -dU
+    args = (K, P, 1.0 / K, c, 0.0, c / K, c * c / K)
+    got = ob.thermodynamic_coefs_compute(n, V, *args)
+    p = O.params_init(n, 10.0, 1e-4, 4.9, 5)
+    assert np.array_equal(np.array([float(got[k]) for k in ob.COEFS]), O.thermo_coefs(p, *args))
+    gamma = 2.0 * n / f
+    k_s = n * T * (1.0 + gamma) / V - 2.0 * c / (9.0 * V)
+    k_t = n * T / V - 2.0 * c / (9.0 * V)
+    want = {"temperature": T, "pressure": P, "Ca_v": f / 2.0, "Ce_v": f / (2.0 * n), "gamma": gamma,
+            "K_S": k_s, "K_T": k_t, "Ca_p": (f / 2.0) * k_s / k_t, "alpha_P": n / (V * k_t),
+            "alpha_S": -1.0 / (gamma * T), "alpha_E1": -3.0 * f / (2.0 * c), "alpha_E2": -3.0 * f / (2.0 * c)}
+    for k, w in want.items():
+        assert abs(float(got[k]) - w) < 1e-8 * abs(w), k   # Ca_v = 1/(1 - (1 - 2/f)) loses ~4 digits
+    with pytest.raises(ValueError):
+        ob.thermodynamic_coefs_compute(n, V, K, (n / V) * T, 1.0 / K, 0.0, 0.0, 0.0, 0.0)
