@@ -5,8 +5,8 @@ Bars: the RDF pair histogram is integer work => BIT-EXACT against the oracle (an
 from it by the same host expressions, equal to the last bit); MSD / VACF are floating-point means whose
 summation order differs from numpy's pairwise sum => 1e-12 relative.
 
-The file name sorts last on purpose: these kernels were written after the round's GPU budget was
-spent, so they run after the already validated suites."""
+The file name sorts last on purpose: these kernels were written at the very end of round 1 (11 of the
+tests below had one hardware run, all green), so they run after the long-validated suites."""
 import importlib
 import os
 
