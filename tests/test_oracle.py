@@ -318,3 +318,53 @@ def test_golden_nlist_n864(O):
     counts, nbr = O.neighbor_list(p, rng, *s[:3], cap=144)
     assert np.array_equal(cell, gn["cell"]) and np.array_equal(start, gn["start"]) and np.array_equal(order, gn["order"])
     assert np.array_equal(counts, gn["counts"]) and np.array_equal(nbr, gn["nbr"].astype(np.int32))
+
+
+@pytest.mark.parametrize("seed,k,L,rc", [(1, 5, 7.6, 2.5), (2, 6, 10.3, 2.5), (3, 6, 12.9, 2.5), (4, 7, 9.1, 2.9),
+                                          (5, 5, 9.0, 3.0)])
+def test_cell_paths_on_random_boxes_with_boundary_atoms(O, seed, k, L, rc):
+    """Randomised cross-check of the cell machinery the GPU large-N path is compared with: jittered
+    lattices in boxes with 3, 4 and 5 cells per edge, some atoms exactly at 0 and exactly at L (wrap can
+    return L).  Cell-list forces / sums == all-pairs oracle (1e-12), neighbour sets == brute force."""
+    rng = np.random.default_rng(seed)
+    n = 4 * k ** 3
+    a = L / k
+    g = (np.arange(k) + 0.25) * a
+    base = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    basis = np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0]]) * a
+    pos = (base[:, None, :] + basis[None, :, :]).reshape(-1, 3) + rng.uniform(-0.12, 0.12, (n, 3)) * a
+    pos = pos - L * np.floor(pos / L)
+    edge = rng.choice(n, 12, replace=False)
+    pos[edge[:6], rng.integers(0, 3, 6)] = 0.0
+    pos[edge[6:], rng.integers(0, 3, 6)] = L
+    x, y, z = [np.ascontiguousarray(pos[:, q]) for q in range(3)]
+    p = O.params_init(n, L, 1e-3, rc, k)
+    nc = O.cells_per_edge(p)
+    if L == 3.0 * rc:
+        # documented back-off: a cell edge within 1e-12 of the range gives up one cell per edge, and two
+        # cells per edge are refused (a 27-cell stencil would visit a neighbour cell twice)
+        assert nc == 2
+        with pytest.raises(O.OracleError):
+            O.compute_lj_cells(p, x, y, z)
+        return
+    assert nc == int(np.floor(L / rc)) and nc >= 3
+    ref = O.compute_lj(p, x, y, z)
+    got = O.compute_lj_cells(p, x, y, z)
+    scale = max(np.abs(ref[q]).max() for q in range(3))
+    for q in range(3):
+        assert np.abs(got[q] - ref[q]).max() < 1e-12 * scale
+    for q in (3, 4, 5):
+        assert abs(got[q] - ref[q]) < 1e-12 * abs(ref[q])
+    assert got[7] == O.count_pairs_in_cutoff(p, x, y, z)
+    # neighbour list with a skin against a brute-force minimum-image search
+    rl = rc + 0.3
+    if O.cells_per_edge_range(p, rl) >= 3:
+        counts, nbr = O.neighbor_list(p, rl, x, y, z, cap=400)
+        d = pos[:, None, :] - pos[None, :, :]
+        d = d - L * np.sign(d * (1.0 / L)) * np.floor(np.abs(d * (1.0 / L)) + 0.5)  # dnint
+        r2 = d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1] + d[..., 2] * d[..., 2]
+        np.fill_diagonal(r2, np.inf)
+        want = r2 < rl * rl
+        assert np.array_equal(counts, want.sum(1).astype(np.int32))
+        for i in list(edge) + [0, n - 1]:
+            assert np.array_equal(nbr[i, :counts[i]], np.nonzero(want[i])[0].astype(np.int32))
