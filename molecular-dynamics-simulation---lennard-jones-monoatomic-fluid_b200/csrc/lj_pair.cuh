@@ -15,9 +15,39 @@ namespace ljmd {
 // for a pair inside the cutoff.  The FMA is exact-equivalent to the reference's separate
 // multiply and subtract whenever L*k is representable (always for |k| <= 2, i.e. for any
 // positions within two boxes of each other; wrapped positions give |k| <= 1).
+//
+// LJMD_MIC_SELECT (build-time experiment for A/B libraries, `make variant DEFS=-DLJMD_MIC_SELECT=1`;
+// default 0): for WRAPPED positions |dx| <= L, so the image shift is 0 or -+L and dx -+ L is the very
+// rounding of the reference's dx - L*(+-1).  The decision |dx| > L/2 can differ from
+// dnint(dx*invL) only where |dx_mic| is within an ulp of L/2 > rc, i.e. for pairs outside the
+// cutoff.  Same FP64-pipe instruction count (=1: DSETP compare) or two fewer per pair component
+// (=2: 64-bit integer compare), and no FRND.F64 (9 cycles each on the pipe MUFU.RCP64H also uses).
+// NOT valid for unwrapped input (|dx| > 1.5 L): never the default.
+#ifndef LJMD_MIC_SELECT
+#define LJMD_MIC_SELECT 0
+#endif
 __device__ __forceinline__ double mic(double dx, double L, double invL)
 {
+#if LJMD_MIC_SELECT == 0
     return fma(-L, rint(dx * invL), dx);
+#else
+    (void)invL;
+    // sign handling on the bit patterns: fabs / negation / copysign of doubles would be emitted as
+    // DADD-with-modifier moves on the FP64 pipe
+    const int hi = __double2hiint(dx), lo = __double2loint(dx);
+    const double neg_l = -L;
+    const double sh = __hiloint2double(__double2hiint(neg_l) ^ (hi & (int)0x80000000), __double2loint(neg_l));
+    const double shifted = __dadd_rn(dx, sh); // dx - L for dx > 0, dx + L for dx < 0
+    const double half = 0.5 * L;              // exact
+#if LJMD_MIC_SELECT == 1
+    const bool far = fabs(dx) > half;
+#else
+    // non-negative doubles order like their bit patterns
+    const unsigned long long mag = ((unsigned long long)((unsigned)hi & 0x7fffffffu) << 32) | (unsigned)lo;
+    const bool far = mag > (unsigned long long)__double_as_longlong(half);
+#endif
+    return __hiloint2double(far ? __double2hiint(shifted) : hi, far ? __double2loint(shifted) : lo);
+#endif
 }
 
 // Squared distance in the reference's order (:129): (dx*dx + dy*dy) + dz*dz, no contraction,
