@@ -650,11 +650,22 @@ nl_step_kernel(NlArgs a)
     bool valid = i < n;
     int nact = gridDim.x, seq = 0, sb = 0, se = n;
     if (SH) {
-        if (a.ctl->halted || a.ctl->steps_left <= 0) return;
         seq = a.ctl->seq;
+        // ONE thread decides for the whole CTA and broadcasts the decision through shared memory.
+        // (Round 1 had every thread test ctl->halted itself: in the launch that raises the halt, CTA 0
+        // sets the flag while other CTAs are starting, so warps of one CTA could disagree -- the warp of
+        // thread 0 left, the others passed the barrier, read a never-written s_viol and advanced their
+        // atoms by a step nobody else took.  That is the rare "wrong velocities in a block of CTAs
+        // around a rebuild" of DESIGN.md section 6.)
         if (threadIdx.x == 0) {
             int viol = 0;
-            if (seq > 0) {
+            const int layer = a.nc * a.nc;
+            const int owned = a.cell_start[a.xhi * layer] - a.cell_start[a.xlo * layer];
+            if (a.ctl->halted || a.ctl->steps_left <= 0) {
+                viol = 2; // nothing to do in this launch
+            } else if ((int)blockIdx.x >= (owned + APB - 1) / APB) {
+                viol = 2; // CTA beyond the owned range (the grid is sized with slack): must not wait for flags
+            } else if (seq > 0) {
                 const int *f = a.flags + (seq & 1) * LJMD_MAX_RANKS;
                 for (int q = 0; q < a.world; ++q) {
                     int v;
@@ -665,6 +676,7 @@ nl_step_kernel(NlArgs a)
             s_viol = viol;
         }
         __syncthreads();
+        if (s_viol & 2) return;
         if (s_viol) { // some atom moved more than skin/2: the list may be stale for this step
             if (blockIdx.x == 0 && threadIdx.x == 0) { a.ctl->halted = 1; a.ctl->need_rebuild = 1; }
             return;
