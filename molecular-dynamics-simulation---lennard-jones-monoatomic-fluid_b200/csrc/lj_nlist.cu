@@ -629,6 +629,9 @@ __device__ __forceinline__ void nl_st_release_sys(int *p, int v)
 #ifndef LJMD_NL_THREADS_SH
 #define LJMD_NL_THREADS_SH 768
 #endif
+#ifndef LJMD_NL_PUBLISH_IN_KERNEL
+#define LJMD_NL_PUBLISH_IN_KERNEL 0 // 1: the last CTA of a sharded step publishes the flags itself
+#endif
 #ifndef LJMD_NL_THREADS_STEP
 #define LJMD_NL_THREADS_STEP 1024
 #endif
@@ -819,8 +822,17 @@ nl_step_kernel(NlArgs a)
             if (!SH) {
                 if (m > a.half_skin2) a.ctl->need_rebuild = 1;
             } else {
-                // "step seq+1 done (+ skin violated)": published to every rank by the next launch
-                a.ctl->pending_flag = ((seq + 1) << 1) | (m > a.half_skin2 ? 1 : 0);
+                // "step seq+1 done (+ skin violated)": published to every rank by nl_publish_kernel
+                const int flag_val = ((seq + 1) << 1) | (m > a.half_skin2 ? 1 : 0);
+                a.ctl->pending_flag = flag_val;
+#if LJMD_NL_PUBLISH_IN_KERNEL
+                // A/B build (`make variant DEFS=-DLJMD_NL_PUBLISH_IN_KERNEL=1`): publish from here and
+                // save one launch per step.  Every CTA fenced its halo stores system-wide before taking
+                // its ticket and this CTA saw all tickets, so the release stores below order them.
+                __threadfence_system();
+                for (int q = 0; q < a.world; ++q)
+                    nl_st_release_sys(a.peer_flags[q] + ((seq + 1) & 1) * LJMD_MAX_RANKS + a.rank, flag_val);
+#endif
                 a.ctl->seq = seq + 1;
                 a.ctl->steps_left -= 1;
                 a.ctl->steps_done += 1;
@@ -1714,11 +1726,13 @@ extern "C" int ljmd_ctx_slab_run(ljmd_ctx *c, int32_t max_steps, int32_t *steps_
     // single-GPU graph path, they never did).
     for (int s = 0; s < max_steps && e == cudaSuccess && rc == LJMD_OK; ++s) {
         rc = nlist_enqueue_step_kernel(c);
+#if !LJMD_NL_PUBLISH_IN_KERNEL
         if (rc == LJMD_OK) {
             const NlArgs a = make_args(c, 0);
             nl_publish_kernel<<<1, 32, 0, c->stream>>>(a);
             c->launches++;
         }
+#endif
     }
     if (e == cudaSuccess) e = cudaEventRecord(c->ev_s1, c->stream);
     NlCtl h;
