@@ -269,6 +269,8 @@ def test_nlist_needs_three_cells(lj):
     assert ei.value.code == 10
 
 
+# a spin-wait kernel that never gets its flag would otherwise hang the GPU box: fail hard instead
+@pytest.mark.timeout(300, method="thread")
 def test_nlist_slab_two_ranks_emulated(lj, O):
     """Slab sharding with two 'ranks' emulated as two contexts on one GPU (peer pointers are the
     other context's device pointers; the all-gather is done by hand with device copies).  One step
