@@ -1788,7 +1788,13 @@ extern "C" int ljmd_ctx_nlist_info(ljmd_ctx *c, double *skin, int32_t *cells_per
         std::vector<int> cnt(c->sc.n);
         cudaError_t e = cudaMemcpy(cnt.data(), c->nw.nb_cnt, sizeof(int) * (size_t)c->sc.n, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = set_error(LJMD_ERR_CUDA, "ljmd_ctx_nlist_info(): %s", cudaGetErrorString(e));
-        for (int v : cnt) total += v;
+        int kb = 0, ke = c->sc.n;
+        if (rc == LJMD_OK && c->nw.sh_on) { // sharded: only the owned slot range has current lists
+            int32_t bounds[LJMD_MAX_RANKS + 1];
+            rc = nlist_slab_bounds_host(c, bounds);
+            if (rc == LJMD_OK) { kb = bounds[c->nw.rank]; ke = bounds[c->nw.rank + 1]; }
+        }
+        for (int k = kb; k < ke; ++k) total += cnt[k];
     }
     if (prev != c->device) cudaSetDevice(prev);
     if (rc != LJMD_OK) return rc;

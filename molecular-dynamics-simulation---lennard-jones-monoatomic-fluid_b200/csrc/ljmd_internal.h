@@ -205,6 +205,7 @@ struct ljmd_ctx {
     // graphs
     cudaGraphExec_t graph_chunk; // G steps
     cudaGraphExec_t graph_compat; // opt-in: one ljmd_verlet_step host-array call (upload, step, download)
+    cudaGraphExec_t graph_tail[16]; // graph_tail[k]: 2k steps (the even remainder of a run after the 32-step chunks)
     int graph_chunk_steps;
     // series buffer
     double *d_series;

@@ -381,7 +381,7 @@ extern "C" int ljmd_time_correlation(const double *ax, const double *ay, const d
     const char *tiled_env = getenv("LJMD_CORR_TILED");
     const int n_orig = (n_snap - 1 + origin_stride - 1) / origin_stride; // len(range(0, n_snap-1, stride))
     const size_t dmat_bytes = sizeof(double) * (size_t)n_orig * (size_t)(max_lag + 1);
-    const bool tiled = tiled_env && atoi(tiled_env) != 0 && n_snap >= 2 && max_lag >= 1 && dmat_bytes <= ((size_t)2 << 30);
+    const bool tiled = !(tiled_env && atoi(tiled_env) == 0) && n_snap >= 2 && max_lag >= 1 && dmat_bytes <= ((size_t)2 << 30);
     DevBuf dmat;
     if (tiled) LJMD_CUDA_CHECK(cudaMalloc(&dmat.p, dmat_bytes));
     EventPair ev;

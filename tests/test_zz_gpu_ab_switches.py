@@ -1,9 +1,8 @@
-"""Parity tests of OPT-IN experiments that were written after round 1's GPU budget was spent and have
-never run on hardware.  Skipped unless LJMD_TEST_EXPERIMENTAL=1, so that the default GPU suite only
-holds validated paths; NOTES_NEXT.md lists them as the first thing to run.
+"""A/B parity of code paths selected by environment switches (each leg in its own process).
 
-* LJMD_COMPAT_GRAPH=1: the drop-in host-array call ljmd_verlet_step replayed as one CUDA graph
-  (upload, drift, force, finalize, download).  Must be bitwise equal to the default path.
+* the drop-in host-array call ljmd_verlet_step is replayed as one CUDA graph (upload, drift, force,
+  finalize, download) by default; LJMD_COMPAT_GRAPH=0 issues the separate launches.  Both must be
+  bitwise equal (first run on a B200 in round 2: green).
 """
 import os
 import subprocess
@@ -12,9 +11,7 @@ import sys
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.skipif(os.environ.get("LJMD_TEST_EXPERIMENTAL", "0") == "0",
-                                 reason="opt-in experiments; set LJMD_TEST_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -48,7 +45,7 @@ def _run(tmp_path, name, env_extra):
 
 
 def test_compat_graph_is_bitwise_equal_to_the_default_drop_in_call(tmp_path):
-    a = _run(tmp_path, "default", {})
-    b = _run(tmp_path, "graph", {"LJMD_COMPAT_GRAPH": "1"})
+    a = _run(tmp_path, "launches", {"LJMD_COMPAT_GRAPH": "0"})
+    b = _run(tmp_path, "graph", {})
     assert np.array_equal(a["obs"], b["obs"])
     assert np.array_equal(a["state"], b["state"])

@@ -144,21 +144,19 @@ def test_msd_ballistic_known_answer_at_production_size(an):
     assert abs(d - v2 * tau[-1] / 3.0) < 1e-9 * d
 
 
-@pytest.mark.skipif(os.environ.get("LJMD_TEST_EXPERIMENTAL", "0") == "0",
-                    reason="opt-in kernel (LJMD_CORR_TILED=1) written after the round's GPU budget was spent; "
-                           "set LJMD_TEST_EXPERIMENTAL=1 to run its parity test")
 @pytest.mark.parametrize("n_snap,n,max_lag,stride", [(70, 77, None, 1), (70, 77, 33, 1), (41, 130, 9, 3),
                                                       (2, 5, None, 1), (300, 500, 200, 5)])
 def test_tiled_time_correlation_is_bit_identical_to_the_default_kernel(an, A, n_snap, n, max_lag, stride):
     rng = np.random.default_rng(n_snap + n)
     v = rng.normal(size=(3, n_snap, n))
     ru = np.cumsum(v, axis=1) * 0.01 + rng.random((3, 1, n)) * 5.0
-    want_m = an.compute_msd_tau_timeorig(*ru, max_lag=max_lag, origin_stride=stride)
-    want_v = an.compute_vacf_tau_timeorig(*v, max_lag=max_lag, origin_stride=stride)
-    os.environ["LJMD_CORR_TILED"] = "1"
+    # the register-tiled kernel is the default; LJMD_CORR_TILED=0 selects the one-warp-per-lag kernel
+    got_m = an.compute_msd_tau_timeorig(*ru, max_lag=max_lag, origin_stride=stride)
+    got_v = an.compute_vacf_tau_timeorig(*v, max_lag=max_lag, origin_stride=stride)
+    os.environ["LJMD_CORR_TILED"] = "0"
     try:
-        got_m = an.compute_msd_tau_timeorig(*ru, max_lag=max_lag, origin_stride=stride)
-        got_v = an.compute_vacf_tau_timeorig(*v, max_lag=max_lag, origin_stride=stride)
+        want_m = an.compute_msd_tau_timeorig(*ru, max_lag=max_lag, origin_stride=stride)
+        want_v = an.compute_vacf_tau_timeorig(*v, max_lag=max_lag, origin_stride=stride)
     finally:
         del os.environ["LJMD_CORR_TILED"]
     assert np.array_equal(got_m, want_m) and np.array_equal(got_v, want_v)
