@@ -83,7 +83,11 @@ enum {
 
 /* Context flags. */
 enum {
-    LJMD_FLAG_TRACK_UNWRAPPED = 1 /* keep ru(t) on the device, md_simulation_program.f90:339-353 */
+    LJMD_FLAG_TRACK_UNWRAPPED = 1, /* keep ru(t) on the device, md_simulation_program.f90:339-353 */
+    LJMD_FLAG_NO_SORT = 2          /* ALLPAIRS: keep the caller's atom order on the device.  By default a large
+                                      sparse-cutoff system (N >= 16384, cutoff sphere < 15 % of the box) is held
+                                      in a spatially sorted order -- upload / download translate, results are
+                                      order independent up to summation order */
 };
 
 typedef struct ljmd_options {
@@ -227,17 +231,10 @@ int ljmd_ctx_slab_run(ljmd_ctx *ctx, int32_t max_steps, int32_t *steps_done, int
 /* Self-check of the neighbour-list path: total momentum (sum of v) of the atoms handled by the last
  * step launch -- an invariant of the dynamics (a sharded run adds the ranks' shares). */
 int ljmd_ctx_nlist_momentum(ljmd_ctx *ctx, double *p3);
-/* Publishes the flag of the last completed step now (normally done by the first CTA of the next
- * step kernel); needed only when ranks are emulated by alternately stepped contexts of ONE process. */
-int ljmd_ctx_slab_publish(ljmd_ctx *ctx);
-/* Debug aid (neighbour-list path): order-independent XOR checksums of {next positions, v, a,
- * packed next positions} over all slots; equal on every rank right after a gather + rebuild. */
-int ljmd_ctx_debug_checksum(ljmd_ctx *ctx, uint64_t *out4);
-
-/* Tuning aid: per-warp {start, end, smid, items} clock records of the last independent-warp
- * all-pairs launch (context created with LJMD_SYM_DEBUG=1); returns the number of warps. */
-int ljmd_ctx_debug_warp_times(ljmd_ctx *ctx, long long *out, int max_warps);
-
+/* A rank that cannot go on (an error from ljmd_ctx_slab_run / _rebuild) tells its peers: its per-step flag
+ * then reads "done, skin violated", so their step kernels halt instead of waiting for it.  (The wait is
+ * bounded anyway: LJMD_SLAB_SPIN_TIMEOUT_S seconds, default 10, then LJMD_ERR_CUDA.) */
+int ljmd_ctx_slab_poison(ljmd_ctx *ctx);
 /* Introspection used by tests and benchmarks. */
 int ljmd_ctx_method(const ljmd_ctx *ctx);          /* resolved LJMD_METHOD_* */
 int ljmd_ctx_cells_per_edge(const ljmd_ctx *ctx);  /* 0 for all-pairs */
@@ -266,12 +263,6 @@ int ljmd_ctx_nlist_info(ljmd_ctx *ctx, double *skin, int32_t *cells_per_edge, in
 int ljmd_ctx_download_nlist(ljmd_ctx *ctx, int32_t *counts, int32_t *nbr, int32_t cap);
 /* Unordered candidate pairs distance-tested / in-cutoff pairs of the last force evaluation. */
 int ljmd_ctx_pair_counts(ljmd_ctx *ctx, int64_t *n_candidates, int64_t *n_in_cutoff);
-
-/* Self-benchmark of the symmetric all-pairs inner routine: cycles per (32 x 32*ri)-pair tile
- * divided by 32, for ri i-atoms per lane and rj rotation offsets per step, seen by one warp when
- * warps_per_cta warps share each SM.  Tuning aid (tools/chunk_cycles.py). */
-int ljmd_bench_chunk_cycles(int32_t ri, int32_t rj, int32_t dense, int32_t warps_per_cta,
-                            double *cycles_per_step);
 
 /* Measured FP64 FMA throughput of the device the context lives on (register-resident DFMA
  * chains), in TFLOP/s; the roofline denominator for the all-pairs kernel. */

@@ -30,6 +30,7 @@ LIB_PATH = os.environ.get("LJMD_LIB_PATH") or os.path.join(_HERE, "lib", "libljm
 
 METHOD_AUTO, METHOD_ALLPAIRS, METHOD_CELLS, METHOD_NLIST = 0, 1, 2, 3
 FLAG_TRACK_UNWRAPPED = 1
+FLAG_NO_SORT = 2
 
 ERR_NAMES = {
     1: "LJMD_ERR_N", 2: "LJMD_ERR_BOX", 3: "LJMD_ERR_VOLUME", 4: "LJMD_ERR_RC",
@@ -84,15 +85,18 @@ ABI_SYMBOLS = [
     "ljmd_ctx_compute_forces", "ljmd_ctx_step", "ljmd_ctx_step_series",
     "ljmd_ctx_kinetic_energy", "ljmd_ctx_method", "ljmd_ctx_cells_per_edge",
     "ljmd_ctx_launch_count", "ljmd_ctx_last_step_ms", "ljmd_ctx_force_timing", "ljmd_ctx_download_cells",
-    "ljmd_ctx_pair_counts", "ljmd_measure_fp64_peak", "ljmd_bench_chunk_cycles",
+    "ljmd_ctx_pair_counts", "ljmd_measure_fp64_peak",
     "ljmd_ctx_set_stream", "ljmd_ctx_device_ptrs", "ljmd_ctx_set_shard", "ljmd_ctx_shard_begin",
-    "ljmd_ctx_shard_step", "ljmd_ctx_shard_end", "ljmd_tail_corrections", "ljmd_ctx_debug_warp_times",
+    "ljmd_ctx_shard_step", "ljmd_ctx_shard_end", "ljmd_tail_corrections",
     "ljmd_ctx_nlist_info", "ljmd_ctx_download_nlist",
     "ljmd_ctx_slab_export", "ljmd_ctx_slab_attach", "ljmd_ctx_slab_bounds", "ljmd_ctx_slab_pack",
     "ljmd_ctx_slab_unpack", "ljmd_ctx_slab_drift", "ljmd_ctx_slab_rebuild", "ljmd_ctx_slab_run",
-    "ljmd_ctx_debug_checksum", "ljmd_ctx_series_arm", "ljmd_ctx_series_fetch", "ljmd_ctx_slab_publish",
+    "ljmd_ctx_slab_poison", "ljmd_ctx_series_arm", "ljmd_ctx_series_fetch",
     "ljmd_ctx_nlist_momentum", "ljmd_rdf_histogram", "ljmd_time_correlation",
 ]
+# Tuning / debug exports declared in csrc/ljmd_debug.h, not in the product header.
+DEBUG_SYMBOLS = ["ljmd_bench_chunk_cycles", "ljmd_ctx_debug_warp_times", "ljmd_ctx_debug_checksum",
+                 "ljmd_ctx_slab_publish"]
 MAX_RANKS = 8
 
 
@@ -176,6 +180,16 @@ class SimState:
         self.__dict__["_addr_cache"] = (arrs, addrs)
         return addrs
 
+    def _addresses_for(self, n: int):
+        """_addresses() after checking that every array holds exactly n values: the C side copies
+        params%n doubles from / to each address (the reference's arrays are allocated with exactly
+        params%n elements, md_types.f90:198-200)."""
+        for k in self.NAMES if n > 0 else ():  # n <= 0 is the C side's error (the reference's own first guard)
+            a = getattr(self, k)
+            if a is None or a.size != n:
+                raise ValueError(f"state.{k} holds {0 if a is None else a.size} values, params%n is {n}")
+        return self._addresses()
+
     def copy(self) -> "SimState":
         s = SimState.__new__(SimState)
         for k in self.NAMES:
@@ -203,7 +217,7 @@ def compute_lj_potential_energy(params: SimParams, state: SimState):
     """physics/lj_potential_energy.f90:46.  Overwrites state.ax/ay/az; returns
     (epot, d_epot, dd_epot)."""
     e, d, dd = C.c_double(), C.c_double(), C.c_double()
-    ad = state._addresses()
+    ad = state._addresses_for(params.n)
     _chk(load_library().ljmd_compute_lj(params, ad[0], ad[1], ad[2], ad[6], ad[7], ad[8], e, d, dd))
     return e.value, d.value, dd.value
 
@@ -212,7 +226,7 @@ def verlet_step(params: SimParams, state: SimState):
     """physics/verlet.f90:41.  Updates all nine arrays in place; returns
     (epot, ekin, d_epot, dd_epot)."""
     e, k, d, dd = C.c_double(), C.c_double(), C.c_double(), C.c_double()
-    _chk(load_library().ljmd_verlet_step(params, *state._addresses(), e, k, d, dd))
+    _chk(load_library().ljmd_verlet_step(params, *state._addresses_for(params.n), e, k, d, dd))
     return e.value, k.value, d.value, dd.value
 
 
@@ -339,6 +353,10 @@ class Context:
 
     def slab_publish(self) -> None:
         _chk(self._L.ljmd_ctx_slab_publish(self._h))
+
+    def slab_poison(self) -> None:
+        """Tell the peer ranks that this rank cannot go on (their step kernels halt instead of waiting)."""
+        _chk(self._L.ljmd_ctx_slab_poison(self._h))
 
     def kinetic_energy(self) -> np.ndarray:
         k = np.zeros(self.nreplicas)

@@ -29,6 +29,7 @@
 // bit-identical to the reference.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "ljmd_internal.h"
@@ -458,6 +459,275 @@ __global__ void __launch_bounds__(512) lj_pairs_symw_kernel(SymArgs a, int n_ite
 }
 
 // ------------------------------------------------------------------------------------------
+// Spatially sorted flavour of the independent-warp kernel (sparse cutoff, large N: the north star's
+// "all-pairs at N = 32k").  Still every unordered pair i<j is distance-tested exactly once, like the
+// reference loop (lj_potential_energy.f90:109-132) -- nothing is skipped -- but the resident atoms are
+// kept in a spatially sorted order (k-d bisection into 32-atom leaves, done by the host at upload;
+// any order gives the same set of pairs), and that makes two things cheap:
+//   * minimum image (geometry_pbc.f90:86).  For a tile (128 i-atoms of a warp) x (32-atom j-chunk)
+//     with bounding-box centres ci, cj and half widths hi, hj, let k = nint((ci-cj)/L) per component
+//     and dx0 = (xi - xj) - L*k.  If |ci - cj - L*k| + hi + hj < L - rc, then for every pair of the
+//     tile either |dx0| < L/2, where k IS the reference's dnint(dx/L) and dx0 is bit-identical to the
+//     reference's dx - L*dnint(dx*invL) (L*k is exact, one rounding in the subtraction), or
+//     |dx0| >= L/2 > rc while the true image is still farther than L - |dx0| > rc: the pair is
+//     outside the cutoff for the reference and for dx0 alike.  So r2 < rc2 takes the reference's
+//     decision for every pair and every in-cutoff pair has the reference's exact dx, dy, dz, r2 --
+//     with ONE add per component (none when k = 0) instead of multiply + round + multiply-subtract.
+//     Tiles that fail the test (never for a sorted homogeneous system) use the general path.
+//   * the interaction stage.  A first pass distance-tests the 4096 pairs of a tile with the j-atom
+//     broadcast from shared memory (no shuffles, 4 independent pairs per lane and j) and only records,
+//     per 32 x 32 sub-tile, whether ANY pair is inside the cutoff (2.6 % of the sub-tiles at rho = 0.8,
+//     rc = 2.5).  Only those sub-tiles run the rotation pass with the interaction body and the j-side
+//     accumulators; its j-side partial is written, and flagged in `near`, only then.
+// Work items are handed out dynamically (atomic counter); every output is indexed by work item or
+// (row, chunk), so results do not depend on which warp ran what: bit-reproducible.
+// ------------------------------------------------------------------------------------------
+struct SortedArgs {
+    SymArgs s;
+    const double *cbox;  // [nchunks][6] centre xyz, half width xyz of every j-chunk
+    unsigned char *near; // [n_rows][nchunks]
+    unsigned *work;      // [2] next item, finished warps
+    int nchunks;
+    double lim;          // L - rc - margin
+    long long rc2_bits;  // bit pattern of rc2: non-negative doubles order like their bit patterns
+};
+
+__global__ void __launch_bounds__(256) chunk_bbox_kernel(int n, const double *rx, const double *ry, const double *rz,
+                                                         double *cbox)
+{
+    const int chunk = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (chunk >= (n + 31) / 32) return;
+    const int j = chunk * 32 + lane;
+    const bool v = j < n;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double lo0 = v ? rx[j] : inf, lo1 = v ? ry[j] : inf, lo2 = v ? rz[j] : inf;
+    double hi0 = v ? lo0 : -inf, hi1 = v ? lo1 : -inf, hi2 = v ? lo2 : -inf;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo0 = fmin(lo0, __shfl_xor_sync(0xffffffffu, lo0, o)); hi0 = fmax(hi0, __shfl_xor_sync(0xffffffffu, hi0, o));
+        lo1 = fmin(lo1, __shfl_xor_sync(0xffffffffu, lo1, o)); hi1 = fmax(hi1, __shfl_xor_sync(0xffffffffu, hi1, o));
+        lo2 = fmin(lo2, __shfl_xor_sync(0xffffffffu, lo2, o)); hi2 = fmax(hi2, __shfl_xor_sync(0xffffffffu, hi2, o));
+    }
+    if (lane == 0) {
+        double *b = cbox + 6 * (size_t)chunk;
+        b[0] = 0.5 * (lo0 + hi0); b[1] = 0.5 * (lo1 + hi1); b[2] = 0.5 * (lo2 + hi2);
+        b[3] = 0.5 * (hi0 - lo0); b[4] = 0.5 * (hi1 - lo1); b[5] = 0.5 * (hi2 - lo2);
+    }
+}
+
+// Pass 1 of a tile: distance test of all 128 x 32 pairs (lj_potential_energy.f90:119-132), j broadcast.
+// SHIFT = false: no component of the tile has an image shift (42 % of the tiles), else one add per
+// component.  Only two variants and a short loop body on purpose: the first version had one variant per
+// shift pattern (8 x 200 instructions) and spent 37 % of its issue slots waiting for instruction fetch
+// (ncu: stall_no_instruction, profiles/r2_ncu_cfg3_sorted_v1.txt).
+// Returns the mask of 32 x 32 sub-tiles (i-atoms r*32 .. r*32+31 of the warp) that hold at least one
+// pair inside the cutoff.
+template <bool SHIFT>
+__device__ __forceinline__ unsigned sorted_far_pass(const double (*sjb)[32], const double (&xi)[4], const double (&yi)[4],
+                                                    const double (&zi)[4], double shx, double shy, double shz,
+                                                    long long rc2b)
+{
+    bool hit[4] = {false, false, false, false};
+#pragma unroll 2
+    for (int jj = 0; jj < 32; ++jj) {
+        const double xj = sjb[0][jj], yj = sjb[1][jj], zj = sjb[2][jj];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            double dx = __dadd_rn(xi[r], -xj), dy = __dadd_rn(yi[r], -yj), dz = __dadd_rn(zi[r], -zj); // :119-121
+            if (SHIFT) { // :124-126, see the header of this section
+                dx = __dadd_rn(dx, shx);
+                dy = __dadd_rn(dy, shy);
+                dz = __dadd_rn(dz, shz);
+            }
+            const double r2 = dist2(dx, dy, dz);                  // :129
+            hit[r] = hit[r] || (__double_as_longlong(r2) < rc2b); // :132 (r2 >= 0: integer compare, off the FP64 pipe)
+        }
+    }
+    unsigned mask = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        if (__any_sync(0xffffffffu, hit[r])) mask |= 1u << r;
+    return mask;
+}
+
+// Pass 2, only for the sub-tiles of `mask`: the rotation scheme of sym_chunk (lane l meets j-atom
+// (l+s)&31, the j-side accumulators rotate through the warp) with the tile's image shift.
+template <bool COUNT>
+__device__ __forceinline__ void sorted_near_pass(unsigned mask, const double (*sjb)[32], const double (&xi)[4],
+                                                 const double (&yi)[4], const double (&zi)[4], double (&fxi)[4],
+                                                 double (&fyi)[4], double (&fzi)[4], double &fjx, double &fjy, double &fjz,
+                                                 double &s12, double &s6, unsigned &ncut, double shx, double shy,
+                                                 double shz, double rc2, int lane)
+{
+    fjx = 0.0; fjy = 0.0; fjz = 0.0;
+#pragma unroll 1
+    for (int s = 0; s < 32; ++s) {
+        const int jj = (lane + s) & 31;
+        const double xj = sjb[0][jj], yj = sjb[1][jj], zj = sjb[2][jj];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (mask & (1u << r)) { // warp-uniform
+                const double dx = __dadd_rn(__dadd_rn(xi[r], -xj), shx);
+                const double dy = __dadd_rn(__dadd_rn(yi[r], -yj), shy);
+                const double dz = __dadd_rn(__dadd_rn(zi[r], -zj), shz);
+                const double r2 = dist2(dx, dy, dz);
+                const bool in = r2 < rc2;
+                if (__any_sync(0xffffffffu, in)) {
+                    double ir2 = fast_rcp(r2);
+                    ir2 = in ? ir2 : 0.0;
+                    const double ir6 = __dmul_rn(__dmul_rn(ir2, ir2), ir2);
+                    const double ir12 = __dmul_rn(ir6, ir6);
+                    s12 = __dadd_rn(s12, ir12);
+                    s6 = __dadd_rn(s6, ir6);
+                    const double g = __dmul_rn(fma(2.0, ir12, -ir6), ir2); // -dU_r / r^2  (:143,148)
+                    fxi[r] = fma(g, dx, fxi[r]); fyi[r] = fma(g, dy, fyi[r]); fzi[r] = fma(g, dz, fzi[r]);
+                    fjx = fma(-g, dx, fjx); fjy = fma(-g, dy, fjy); fjz = fma(-g, dz, fjz);
+                    if (COUNT) ncut += in ? 1u : 0u;
+                }
+            }
+        }
+        fjx = __shfl_sync(0xffffffffu, fjx, (lane + 1) & 31);
+        fjy = __shfl_sync(0xffffffffu, fjy, (lane + 1) & 31);
+        fjz = __shfl_sync(0xffffffffu, fjz, (lane + 1) & 31);
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(512) lj_pairs_sorted_kernel(SortedArgs A, int n_items)
+{
+    constexpr int RI = 4, TI = RI * 32, MAXW = 16;
+    const SymArgs &a = A.s;
+    __shared__ double sj[MAXW][2][3][32];
+    const int NW = blockDim.x >> 5;
+    const int n = a.sc.n;
+    const double *rx = a.rx, *ry = a.ry, *rz = a.rz;
+    const double L = a.sc.L, invL = a.sc.invL, rc2 = a.sc.rc2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double (*sjw)[3][32] = sj[warp];
+    unsigned ncut = 0;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+
+    for (;;) {
+        int it = 0;
+        if (lane == 0) it = (int)atomicAdd(&A.work[0], 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= n_items) break;
+        const int4 item = a.items[it];
+        const int row = item.x, chunk0 = item.y, nchunks = item.z, split = item.w;
+        const int iw0 = row * TI;
+        double xi[RI], yi[RI], zi[RI], fxi[RI], fyi[RI], fzi[RI];
+        double lo0 = inf, lo1 = inf, lo2 = inf, hi0 = -inf, hi1 = -inf, hi2 = -inf;
+#pragma unroll
+        for (int r = 0; r < RI; ++r) {
+            const int ig = iw0 + r * 32 + lane;
+            const bool v = ig < n;
+            xi[r] = v ? rx[ig] : 0.0; yi[r] = v ? ry[ig] : 0.0; zi[r] = v ? rz[ig] : 0.0;
+            fxi[r] = 0.0; fyi[r] = 0.0; fzi[r] = 0.0;
+            if (v) {
+                lo0 = fmin(lo0, xi[r]); hi0 = fmax(hi0, xi[r]);
+                lo1 = fmin(lo1, yi[r]); hi1 = fmax(hi1, yi[r]);
+                lo2 = fmin(lo2, zi[r]); hi2 = fmax(hi2, zi[r]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo0 = fmin(lo0, __shfl_xor_sync(0xffffffffu, lo0, o)); hi0 = fmax(hi0, __shfl_xor_sync(0xffffffffu, hi0, o));
+            lo1 = fmin(lo1, __shfl_xor_sync(0xffffffffu, lo1, o)); hi1 = fmax(hi1, __shfl_xor_sync(0xffffffffu, hi1, o));
+            lo2 = fmin(lo2, __shfl_xor_sync(0xffffffffu, lo2, o)); hi2 = fmax(hi2, __shfl_xor_sync(0xffffffffu, hi2, o));
+        }
+        const double cix = 0.5 * (lo0 + hi0), ciy = 0.5 * (lo1 + hi1), ciz = 0.5 * (lo2 + hi2);
+        const double hix = 0.5 * (hi0 - lo0), hiy = 0.5 * (hi1 - lo1), hiz = 0.5 * (hi2 - lo2);
+        double s12 = 0.0, s6 = 0.0;
+        {
+            const int jg = chunk0 * 32 + lane;
+            const bool v = jg < n;
+            __syncwarp();
+            sjw[0][0][lane] = v ? rx[jg] : 0.0;
+            sjw[0][1][lane] = v ? ry[jg] : 0.0;
+            sjw[0][2][lane] = v ? rz[jg] : 0.0;
+            __syncwarp();
+        }
+        // centre / half width of the current chunk, one component per lane (lanes 0..5)
+        double bcur = (lane < 6) ? A.cbox[6 * (size_t)chunk0 + lane] : 0.0;
+        for (int k = 0; k < nchunks; ++k) {
+            const int buf = k & 1;
+            const int chunk = chunk0 + k, j0 = chunk * 32;
+            double px = 0.0, py = 0.0, pz = 0.0, bnext = 0.0; // next chunk, in flight during the compute
+            if (k + 1 < nchunks) {
+                const int jg = j0 + 32 + lane;
+                if (jg < n) { px = rx[jg]; py = ry[jg]; pz = rz[jg]; }
+                if (lane < 6) bnext = A.cbox[6 * (size_t)(chunk + 1) + lane];
+            }
+            double fjx = 0.0, fjy = 0.0, fjz = 0.0;
+            bool wrote = true;
+            const bool all = (j0 >= iw0 + TI) && (j0 + 32 <= n);
+            bool general = !all; // diagonal / ragged tile, or a tile that fails the shift test: general path
+            double shx = 0.0, shy = 0.0, shz = 0.0;
+            if (all) {
+                // image shift of the tile and the test that makes it valid (header of this section)
+                const double cjx = __shfl_sync(0xffffffffu, bcur, 0), cjy = __shfl_sync(0xffffffffu, bcur, 1),
+                             cjz = __shfl_sync(0xffffffffu, bcur, 2), hjx = __shfl_sync(0xffffffffu, bcur, 3),
+                             hjy = __shfl_sync(0xffffffffu, bcur, 4), hjz = __shfl_sync(0xffffffffu, bcur, 5);
+                const double cx = cix - cjx, cy = ciy - cjy, cz = ciz - cjz;
+                shx = -(L * rint(cx * invL)); shy = -(L * rint(cy * invL)); shz = -(L * rint(cz * invL));
+                general = !((fabs(cx + shx) + (hix + hjx) < A.lim) && (fabs(cy + shy) + (hiy + hjy) < A.lim) &&
+                            (fabs(cz + shz) + (hiz + hjz) < A.lim));
+            }
+            if (general) {
+                // one instantiation for both cases: the per-pair masks of the diagonal variant (j > i, j < n)
+                // are all true for a full off-diagonal tile
+                sym_chunk<RI, 1, true, false, COUNT>(sjw[buf], xi, yi, zi, fxi, fyi, fzi, fjx, fjy, fjz, s12, s6, ncut, L,
+                                                     invL, rc2, lane, iw0, j0, n);
+            } else {
+                const bool noshift = (shx == 0.0) && (shy == 0.0) && (shz == 0.0);
+                const unsigned mask = noshift ? sorted_far_pass<false>(sjw[buf], xi, yi, zi, shx, shy, shz, A.rc2_bits)
+                                              : sorted_far_pass<true>(sjw[buf], xi, yi, zi, shx, shy, shz, A.rc2_bits);
+                if (mask) sorted_near_pass<COUNT>(mask, sjw[buf], xi, yi, zi, fxi, fyi, fzi, fjx, fjy, fjz, s12, s6, ncut,
+                                                  shx, shy, shz, rc2, lane);
+                else wrote = false;
+            }
+            if (wrote) { // lane l holds the j-side force of atom j0 + l
+                const int jg = j0 + lane;
+                if (jg < n) {
+                    double *fj = a.fJ + (size_t)row * 3 * n;
+                    fj[jg] = fjx; fj[(size_t)n + jg] = fjy; fj[2 * (size_t)n + jg] = fjz;
+                }
+            }
+            if (lane == 0) A.near[(size_t)row * A.nchunks + chunk] = wrote ? 1 : 0;
+            if (k + 1 < nchunks) {
+                sjw[buf ^ 1][0][lane] = px; sjw[buf ^ 1][1][lane] = py; sjw[buf ^ 1][2][lane] = pz;
+            }
+            bcur = bnext;
+            __syncwarp();
+        }
+#pragma unroll
+        for (int r = 0; r < RI; ++r) {
+            const int ig = iw0 + r * 32 + lane;
+            if (ig < n) {
+                double *fp = a.fI + (size_t)split * 3 * n;
+                fp[ig] = fxi[r]; fp[(size_t)n + ig] = fyi[r]; fp[2 * (size_t)n + ig] = fzi[r];
+            }
+        }
+        // scalar partials per WORK ITEM (not per warp: which warp ran the item varies run to run)
+        s12 = warp_sum(s12);
+        s6 = warp_sum(s6);
+        if (lane == 0) {
+            double *sp = a.spart + (size_t)it * 3;
+            sp[0] = s12; sp[1] = s6; sp[2] = 0.0;
+        }
+    }
+    if (COUNT) {
+        const unsigned c = __reduce_add_sync(0xffffffffu, ncut);
+        if (lane == 0 && a.pair_counts) atomicAdd(&a.pair_counts[1], (unsigned long long)c);
+    }
+    if (lane == 0) { // the last warp to run dry re-arms the counters for the next launch
+        __threadfence();
+        const unsigned d = atomicAdd(&A.work[1], 1u);
+        if (d == gridDim.x * NW - 1) { A.work[0] = 0u; A.work[1] = 0u; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Self-benchmark of the inner routine: `nw` warps per CTA, one CTA per SM, each warp runs
 // `reps` chunks (32 rotation steps each) on synthetic in-cutoff data; reports the cycles per
 // rotation step seen by warp 0 of CTA 0 (clock64).  Used to size RI / warps per SM.
@@ -588,6 +858,12 @@ int pairwork_plan(ljmd_ctx *c)
         if (const char *e = getenv("LJMD_SYM_W")) w.warps = atoi(e);
         w.rj = (n >= 16384) ? 1 : 2;
         if (const char *e = getenv("LJMD_SYM_RJ")) w.rj = atoi(e);
+        // Sparse cutoff at large N: spatially sorted state + lj_pairs_sorted_kernel (rows of 128 atoms,
+        // independent warps).  Needs one j-side partial plane per row: n_rows * 3 * n doubles.
+        w.sorted = n >= 16384 && !w.dense && c->R == 1 && (c->o.flags & LJMD_FLAG_NO_SORT) == 0;
+        if (const char *e = getenv("LJMD_SYM_SORTED")) w.sorted = w.sorted && atoi(e) != 0;
+        if (w.sorted && sizeof(double) * 3.0 * n * ((n + 127) / 128) > 2.0 * 1073741824.0) w.sorted = false;
+        if (w.sorted) { w.ri = 4; w.warps = 1; w.rj = 1; }
         // small systems: independent warps (rows of ri*32 atoms) packed into fat CTAs
         w.indep = (w.warps == 1);
         w.cta_warps = 16;
@@ -627,6 +903,32 @@ int pairwork_plan(ljmd_ctx *c)
             if (kr < 1) kr = 1;
             if (kr > m) kr = m;
             int c0 = first;
+            if (w.sorted) {
+                // 32-chunk items, then the rest of the row in pieces of <= 8 chunks: the items are handed
+                // out dynamically, longest first, so the short ones level the tail
+                // Pieces of 32 chunks from the diagonal outwards (the near-diagonal pieces carry the
+                // interaction work), and the far end of the row in ever smaller pieces: the items are handed out
+                // dynamically, longest first, so the small ones level the tail (a 128 x 32 tile is ~2 us of one
+                // warp when four warps share an FP64 pipe)
+                static const int tail_pieces[] = {16, 8, 8, 4, 4, 2, 2, 2, 1, 1};
+                int left = m, s = 0;
+                while (left > 48 + 32) { items.push_back(make_int4(r, c0, 32, s++)); c0 += 32; left -= 32; }
+                for (int q = 0; q < 10 && left > 48; ++q) { // left in (48, 80]: one more variable piece
+                    const int len = left - 48;
+                    items.push_back(make_int4(r, c0, len, s++));
+                    c0 += len; left -= len;
+                    break;
+                }
+                for (int q = 0; q < 10 && left > 0; ++q) {
+                    const int len = std::min(left, tail_pieces[q]);
+                    items.push_back(make_int4(r, c0, len, s++));
+                    c0 += len; left -= len;
+                }
+                if (left > 0) { items.push_back(make_int4(r, c0, left, s++)); c0 += left; left = 0; }
+                kr = 0; // nothing left for the generic splitter below
+                row_splits[r] = s;
+                max_splits = std::max(max_splits, s);
+            }
             for (int s = 0; s < (int)kr; ++s) {
                 const int len = m / (int)kr + (s < m % (int)kr ? 1 : 0);
                 int4 it;
@@ -634,8 +936,10 @@ int pairwork_plan(ljmd_ctx *c)
                 items.push_back(it);
                 c0 += len;
             }
-            row_splits[r] = (int)kr;
-            max_splits = std::max(max_splits, (int)kr);
+            if (!w.sorted) {
+                row_splits[r] = (int)kr;
+                max_splits = std::max(max_splits, (int)kr);
+            }
         }
         w.chunks_per_item = 0; // unused: per-row split counts live in w.row_splits
         LJMD_CUDA_CHECK(cudaMalloc(&w.row_splits, sizeof(int) * w.n_rows));
@@ -645,7 +949,16 @@ int pairwork_plan(ljmd_ctx *c)
         w.n_items = (int)items.size();
         w.n_splits = max_splits;
         w.n_ctas = w.n_items;
-        if (w.indep) {
+        if (w.sorted) {
+            w.n_ctas = sms;
+            w.cta_warps = 16;
+            const int nch = (n + 31) / 32;
+            LJMD_CUDA_CHECK(cudaMalloc(&w.cbox, sizeof(double) * 6 * (size_t)nch));
+            LJMD_CUDA_CHECK(cudaMalloc(&w.near, (size_t)w.n_rows * nch));
+            LJMD_CUDA_CHECK(cudaMemsetAsync(w.near, 0, (size_t)w.n_rows * nch, c->stream));
+            LJMD_CUDA_CHECK(cudaMalloc(&w.work, sizeof(unsigned) * 2));
+            LJMD_CUDA_CHECK(cudaMemsetAsync(w.work, 0, sizeof(unsigned) * 2, c->stream));
+        } else if (w.indep) {
             // fat CTAs of 16 independent warps, one CTA per SM when there is enough work
             int ctas = (w.n_items + 15) / 16;
             if (c->R == 1) ctas = std::min(ctas, sms);
@@ -668,7 +981,7 @@ int pairwork_plan(ljmd_ctx *c)
         LJMD_CUDA_CHECK(cudaMalloc(&w.dbg, sizeof(long long) * 4 * (size_t)w.n_ctas * w.cta_warps));
         LJMD_CUDA_CHECK(cudaMemset(w.dbg, 0, sizeof(long long) * 4 * (size_t)w.n_ctas * w.cta_warps));
     }
-    w.n_spart = (w.variant == 1 && w.indep) ? w.n_ctas : w.n_items;
+    w.n_spart = (w.variant == 1 && w.indep && !w.sorted) ? w.n_ctas : w.n_items;
     const size_t sbytes = sizeof(double) * (size_t)c->R * w.n_spart * 3;
     LJMD_CUDA_CHECK(cudaMalloc(&w.spart, sbytes));
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.spart, 0, sbytes, c->stream));
@@ -721,8 +1034,22 @@ int launch_pairs(ljmd_ctx *c, int buf)
         a.n_rows = w.n_rows;
         a.pair_counts = c->fw.pair_counts;
         a.dbg = w.dbg;
-        const int key = (w.indep ? 10000 : 0) + w.ri * 1000 + w.rj * 100 + (w.indep ? 0 : w.warps);
+        const int key = w.sorted ? -1 : (w.indep ? 10000 : 0) + w.ri * 1000 + w.rj * 100 + (w.indep ? 0 : w.warps);
         switch (key) {
+        case -1: {
+            SortedArgs A;
+            A.s = a;
+            A.cbox = w.cbox; A.near = w.near; A.work = w.work;
+            A.nchunks = (c->sc.n + 31) / 32;
+            A.lim = (c->sc.L - c->p.rc) * (1.0 - 1e-9);
+            const double rc2 = c->sc.rc2;
+            memcpy(&A.rc2_bits, &rc2, sizeof(double));
+            chunk_bbox_kernel<<<(A.nchunks * 32 + 255) / 256, 256, 0, c->stream>>>(c->sc.n, px, py, pz, w.cbox);
+            if (a.pair_counts) lj_pairs_sorted_kernel<true><<<w.n_ctas, 512, 0, c->stream>>>(A, w.n_items);
+            else lj_pairs_sorted_kernel<false><<<w.n_ctas, 512, 0, c->stream>>>(A, w.n_items);
+            if (!c->capturing) c->launches++;
+            break;
+        }
         case 12100: launch_symw<2, 1>(c, a); break;
         case 12200: launch_symw<2, 2>(c, a); break;
         case 11400: launch_symw<1, 4>(c, a); break;

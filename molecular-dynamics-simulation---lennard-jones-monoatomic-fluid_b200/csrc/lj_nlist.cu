@@ -91,6 +91,7 @@ struct NlArgs {
     int *peer_flags[LJMD_MAX_RANKS];  // flag block ([2][LJMD_MAX_RANKS] ints) of every rank
     int *flags;                       // this rank's flag block (the peers write into it)
     int *dbg_exec;                    // debug: CTAs that executed the body of sharded step seq (or nullptr)
+    unsigned long long spin_budget_ns; // longest wait for the peers' flags before the run is declared dead
     int eval_sel;  // rebuild kernels: 0 = the list is for rb[cur], 1 = for rb[1-cur]
     unsigned long long *pair_counts;
 };
@@ -610,6 +611,15 @@ __device__ __forceinline__ int nl_ld_acquire_sys(const int *p)
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long nl_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr int NL_ERR_FLAG_TIMEOUT = 0x20000000; // NlCtl::overflow code: a peer's per-step flag never arrived
+constexpr int NL_ERR_OWN_BLOCKS = 0x40000000;   // NlCtl::overflow code: more owned atoms than the launch has CTAs for
+constexpr int NL_FLAG_POISON = 0x7fffffff;      // flag value of a rank that failed: "every step done, skin violated"
 __device__ __forceinline__ void nl_st_release_sys(int *p, int v)
 {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -664,16 +674,28 @@ nl_step_kernel(NlArgs a)
             int viol = 0;
             const int layer = a.nc * a.nc;
             const int owned = a.cell_start[a.xhi * layer] - a.cell_start[a.xlo * layer];
-            if (a.ctl->halted || a.ctl->steps_left <= 0) {
-                viol = 2; // nothing to do in this launch
+            if (a.ctl->halted || a.ctl->steps_left <= 0 || a.ctl->overflow != 0) {
+                viol = 2; // nothing to do in this launch (a list overflow freezes the state at the last valid step)
             } else if ((int)blockIdx.x >= (owned + APB - 1) / APB) {
                 viol = 2; // CTA beyond the owned range (the grid is sized with slack): must not wait for flags
             } else if (seq > 0) {
+                // Wait for every rank's flag of step seq, but never forever: a peer that died, stopped
+                // launching after an error or was given another step count would otherwise leave this GPU
+                // spinning until a reset.  On expiry the run halts with NL_ERR_FLAG_TIMEOUT (the host
+                // reports LJMD_ERR_CUDA); a failing rank also publishes a poison flag (NL_FLAG_POISON).
                 const int *f = a.flags + (seq & 1) * LJMD_MAX_RANKS;
-                for (int q = 0; q < a.world; ++q) {
+                const unsigned long long t0 = nl_globaltimer();
+                for (int q = 0; q < a.world && viol != 2; ++q) {
                     int v;
-                    while (((v = nl_ld_acquire_sys(f + q)) >> 1) < seq) __nanosleep(40);
-                    viol |= v & 1;
+                    while (((v = nl_ld_acquire_sys(f + q)) >> 1) < seq) {
+                        __nanosleep(40);
+                        if (nl_globaltimer() - t0 > a.spin_budget_ns) { viol = 2; break; }
+                    }
+                    if (viol != 2) viol |= v & 1;
+                }
+                if (viol == 2) { // timed out: freeze this rank (every CTA of this and later launches leaves at once)
+                    atomicMax(&a.ctl->overflow, NL_ERR_FLAG_TIMEOUT);
+                    a.ctl->halted = 1;
                 }
             }
             s_viol = viol;
@@ -689,7 +711,7 @@ nl_step_kernel(NlArgs a)
         se = a.cell_start[a.xhi * layer];
         nact = (se - sb + APB - 1) / APB;
         if (nact > (int)gridDim.x) { // more owned atoms than the launch has CTAs for: flagged, reported by the host
-            if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(&a.ctl->overflow, 0x40000000);
+            if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(&a.ctl->overflow, NL_ERR_OWN_BLOCKS);
             nact = gridDim.x;
         }
         if ((int)blockIdx.x >= nact) return;
@@ -697,6 +719,11 @@ nl_step_kernel(NlArgs a)
         valid = i < se;
         if (a.dbg_exec && threadIdx.x == 0 && seq < 4096) atomicAdd(&a.dbg_exec[seq], 1);
     }
+    // A neighbour-list overflow (an atom with more neighbours than the capacity: its list was truncated)
+    // freezes the state: the step is a no-op for every thread, so nothing is advanced with missing
+    // interactions and the host finds the last valid step when it reports the error.  The flag is only
+    // raised by the build kernels, which precede this launch in stream order: every thread reads the same value.
+    if (!SH && MODE == 1 && a.ctl->overflow != 0) return;
     const int cur = a.ctl->cur;
     const int ev = (MODE == 1) ? 1 - cur : cur;
     const double4 *pos = a.p4[ev];
@@ -1074,6 +1101,10 @@ static NlArgs make_args(ljmd_ctx *c, int eval_sel)
     for (int q = 0; q < LJMD_MAX_RANKS; ++q) { a.peer_p4[q] = w.peer_p4[q]; a.peer_flags[q] = w.peer_flags[q]; }
     a.flags = w.flags;
     a.dbg_exec = w.dbg_exec;
+    {
+        static const double budget_s = getenv("LJMD_SLAB_SPIN_TIMEOUT_S") ? atof(getenv("LJMD_SLAB_SPIN_TIMEOUT_S")) : 10.0;
+        a.spin_budget_ns = (unsigned long long)((budget_s > 0.0 ? budget_s : 10.0) * 1e9);
+    }
     if (w.sh_on) { a.sc.tail_u = 0.0; a.sc.tail_du = 0.0; a.sc.tail_ddu = 0.0; } // added once, after the cross-rank reduction
     return a;
 }
@@ -1381,12 +1412,17 @@ int nlist_check_overflow(ljmd_ctx *c)
     LJMD_CUDA_CHECK(cudaMemcpyAsync(&h, c->nw.ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     c->nw.rebuilds_host = h.rebuilds;
-    if (h.overflow >= 0x40000000)
+    if (h.overflow != 0) c->nw.cur_host = h.cur; // step launches after the error were no-ops: follow the device
+    if (h.overflow >= NL_ERR_OWN_BLOCKS)
         return set_error(LJMD_ERR_UNSUPPORTED, "slab sharding: a rank owns more atoms than its launch capacity (density too inhomogeneous)");
+    if (h.overflow >= NL_ERR_FLAG_TIMEOUT)
+        return set_error(LJMD_ERR_CUDA, "slab sharding: a peer rank's per-step flag did not arrive within the spin budget "
+                                        "(LJMD_SLAB_SPIN_TIMEOUT_S); the run is halted, the state is at the last completed step");
     if (h.overflow > 0)
         return set_error(LJMD_ERR_UNSUPPORTED,
                          "neighbour list capacity exceeded: an atom has %d neighbours within rc+skin, capacity %d "
-                         "(set LJMD_NL_CAP)", h.overflow, c->nw.maxnb);
+                         "(set LJMD_NL_CAP); stepping stopped at the last valid step -- re-create the context with a "
+                         "larger capacity and upload again", h.overflow, c->nw.maxnb);
     return LJMD_OK;
 }
 
@@ -1660,6 +1696,31 @@ extern "C" int ljmd_ctx_slab_publish(ljmd_ctx *c)
     return LJMD_OK;
 }
 
+__global__ void nl_poison_kernel(NlArgs a)
+{
+    if (threadIdx.x != 0) return;
+    __threadfence_system();
+    for (int q = 0; q < a.world; ++q)
+        for (int par = 0; par < 2; ++par) nl_st_release_sys(a.peer_flags[q] + par * LJMD_MAX_RANKS + a.rank, NL_FLAG_POISON);
+}
+
+// A rank that cannot go on (an error return from ljmd_ctx_slab_run / _rebuild) tells its peers: its flag reads
+// "every step done, skin violated", so the peers' step kernels halt at once instead of waiting for it.
+extern "C" int ljmd_ctx_slab_poison(ljmd_ctx *c)
+{
+    if (!c || !c->nw.sh_on) return set_error(LJMD_ERR_ARG, "ljmd_ctx_slab_poison(): context is not sharded.");
+    int prev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
+    const NlArgs a = make_args(c, 0);
+    nl_poison_kernel<<<1, 32, 0, c->stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (prev != c->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return set_error(LJMD_ERR_CUDA, "ljmd_ctx_slab_poison(): %s", cudaGetErrorString(e));
+    return LJMD_OK;
+}
+
 // Debug aid: XOR checksums of {next positions, v, a, packed next positions} over ALL slots.
 extern "C" int ljmd_ctx_debug_checksum(ljmd_ctx *c, uint64_t *out4)
 {
@@ -1720,10 +1781,10 @@ extern "C" int ljmd_ctx_slab_run(ljmd_ctx *c, int32_t max_steps, int32_t *steps_
                                     cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaEventRecord(c->ev_s0, c->stream);
     // Every step kernel is followed by the 1-thread publish kernel: the kernel boundary guarantees
-    // that all halo stores of the step are performed system-wide before its flag becomes visible,
-    // and two step kernels are never adjacent in the stream (back-to-back step kernels were observed
-    // to produce rare wrong velocities on B200; with a small kernel in between, as in the
-    // single-GPU graph path, they never did).
+    // that all halo stores of the step are performed system-wide before its flag becomes visible.
+    // (The rare wrong-velocity defect once blamed on adjacent step kernels had another cause -- every
+    // thread tested ctl->halted itself -- fixed in the sharded prologue of nl_step_kernel, DESIGN.md 6.
+    // LJMD_NL_PUBLISH_IN_KERNEL=1 builds publish from the step kernel's last CTA instead.)
     for (int s = 0; s < max_steps && e == cudaSuccess && rc == LJMD_OK; ++s) {
         rc = nlist_enqueue_step_kernel(c);
 #if !LJMD_NL_PUBLISH_IN_KERNEL

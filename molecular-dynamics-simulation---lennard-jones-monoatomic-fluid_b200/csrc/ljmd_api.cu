@@ -9,8 +9,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <algorithm>
 #include <mutex>
 #include <new>
+#include <numeric>
+#include <vector>
 
 #include "ljmd_internal.h"
 
@@ -94,13 +97,77 @@ struct DeviceGuard {
     ~DeviceGuard() { if (active) cudaSetDevice(prev); }
 };
 
+// ------------------------------------------------------------------------------------------
+// Spatial order of the sorted all-pairs path (lj_allpairs.cu: lj_pairs_sorted_kernel): recursive
+// bisection at the median of the widest extent, left part a multiple of 128 atoms (32 below 128),
+// down to leaves of 32 atoms = the j-chunks; inside a leaf atoms keep their original order.
+// Deterministic (ties broken by atom index).  Any order is CORRECT -- the kernel tests every pair
+// and verifies its per-tile assumptions -- this one only makes the tiles compact.
+// ------------------------------------------------------------------------------------------
+static void kd_order_rec(int *idx, int m, const double *x, const double *y, const double *z)
+{
+    if (m <= 32) { std::sort(idx, idx + m); return; }
+    const int unit = m > 128 ? 128 : 32;
+    const int nu = (m + unit - 1) / unit;
+    int nl = ((nu + 1) / 2) * unit;
+    if (nl > m - 1) nl = m - 1;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    const double *c3[3] = {x, y, z};
+    for (int k = 0; k < m; ++k)
+        for (int d = 0; d < 3; ++d) {
+            const double v = c3[d][idx[k]];
+            lo[d] = std::min(lo[d], v);
+            hi[d] = std::max(hi[d], v);
+        }
+    int d = 0;
+    if (hi[1] - lo[1] > hi[d] - lo[d]) d = 1;
+    if (hi[2] - lo[2] > hi[d] - lo[d]) d = 2;
+    const double *cd = c3[d];
+    std::nth_element(idx, idx + nl, idx + m, [cd](int a, int b) { return cd[a] < cd[b] || (cd[a] == cd[b] && a < b); });
+    kd_order_rec(idx, nl, x, y, z);
+    kd_order_rec(idx + nl, m - nl, x, y, z);
+}
+
+static int compute_sort_perm(ljmd_ctx *c, const double *x, const double *y, const double *z)
+{
+    const int n = c->sc.n;
+    if (!c->pw.perm) {
+        c->pw.perm = (int *)malloc(sizeof(int) * (size_t)n);
+        if (!c->pw.perm) return set_error(LJMD_ERR_NOMEM, "out of host memory (sort permutation).");
+    }
+    std::iota(c->pw.perm, c->pw.perm + n, 0);
+    bool finite = true;
+    for (int k = 0; k < n && finite; ++k) finite = std::isfinite(x[k]) && std::isfinite(y[k]) && std::isfinite(z[k]);
+    if (finite) kd_order_rec(c->pw.perm, n, x, y, z); // NaN / Inf input: keep the caller's order (the reference does not guard either)
+    c->pw.steps_since_sort = 0;
+    return LJMD_OK;
+}
+
+// host array (caller's order) -> pinned stage (device order) and back
+static void stage_in(const ljmd_ctx *c, double *dst, const double *src)
+{
+    const size_t n = c->nR;
+    if (const int *pm = c->pw.perm) for (size_t k = 0; k < n; ++k) dst[k] = src[pm[k]];
+    else memcpy(dst, src, sizeof(double) * n);
+}
+static void stage_out(const ljmd_ctx *c, double *dst, const double *src)
+{
+    const size_t n = c->nR;
+    if (const int *pm = c->pw.perm) for (size_t k = 0; k < n; ++k) dst[pm[k]] = src[k];
+    else memcpy(dst, src, sizeof(double) * n);
+}
+
 static int enqueue_force(ljmd_ctx *c, int buf)
 {
     if (c->method == LJMD_METHOD_CELLS) return launch_cells_force(c, buf);
     return launch_pairs(c, buf);
 }
 
-static int kernels_per_step(const ljmd_ctx *c) { return (c->method == LJMD_METHOD_CELLS) ? c->cw.kernels_per_force + 1 : 2; }
+static int kernels_per_step(const ljmd_ctx *c)
+{
+    if (c->method == LJMD_METHOD_CELLS) return c->cw.kernels_per_force + 1;
+    return c->pw.sorted ? 3 : 2; // (chunk boxes +) force + finalize
+}
 
 // One velocity-Verlet step.  On entry rbuf[prev] holds r(t) and rbuf[1-prev] already holds the
 // drifted + wrapped r(t+dt).  fin_mode 1 leaves r(t+2dt) in rbuf[prev]; fin_mode 2 copies r(t+dt)
@@ -337,6 +404,10 @@ extern "C" int ljmd_ctx_destroy(ljmd_ctx *c)
     cudaFree(c->pw.items);
     cudaFree(c->pw.row_splits);
     cudaFree(c->pw.dbg);
+    cudaFree(c->pw.cbox);
+    cudaFree(c->pw.near);
+    cudaFree(c->pw.work);
+    free(c->pw.perm);
     cudaFree(c->fw.kpart);
     cudaFree(c->fw.counter);
     cudaFree(c->fw.ctl);
@@ -479,12 +550,16 @@ extern "C" int ljmd_ctx_upload(ljmd_ctx *c, const double *rx, const double *ry, 
     if (c->method == LJMD_METHOD_NLIST) LJMD_TRY(nlist_canonicalize(c));
     const double *src[9] = {rx, ry, rz, vx, vy, vz, ax, ay, az};
     const size_t bytes = sizeof(double) * c->nR;
+    // sorted all-pairs path: a COMPLETE upload defines a new spatial order; a partial one keeps the
+    // current order (the arrays it leaves alone are already on the device in that order)
+    if (c->method == LJMD_METHOD_ALLPAIRS && c->pw.sorted && rx && ry && rz && vx && vy && vz && ax && ay && az)
+        LJMD_TRY(compute_sort_perm(c, rx, ry, rz));
     // pack contiguous runs of non-NULL arrays into the pinned stage, one H2D per run
     int k = 0;
     while (k < 9) {
         if (!src[k]) { ++k; continue; }
         int e = k;
-        while (e < 9 && src[e]) { memcpy(c->h_stage + (size_t)e * c->nR, src[e], bytes); ++e; }
+        while (e < 9 && src[e]) { stage_in(c, c->h_stage + (size_t)e * c->nR, src[e]); ++e; }
         LJMD_CUDA_CHECK(cudaMemcpyAsync(c->state_block + (size_t)k * c->nR,
                                         c->h_stage + (size_t)k * c->nR, bytes * (e - k),
                                         cudaMemcpyHostToDevice, c->stream));
@@ -525,7 +600,7 @@ extern "C" int ljmd_ctx_download(ljmd_ctx *c, double *rx, double *ry, double *rz
     }
     LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     for (k = 0; k < 9; ++k)
-        if (dst[k]) memcpy(dst[k], c->h_stage + (size_t)k * c->nR, bytes);
+        if (dst[k]) stage_out(c, dst[k], c->h_stage + (size_t)k * c->nR);
     return LJMD_OK;
 }
 
@@ -543,6 +618,15 @@ extern "C" int ljmd_ctx_download_unwrapped(ljmd_ctx *c, double *rux, double *ruy
     if (c->method == LJMD_METHOD_NLIST) {
         LJMD_TRY(nlist_gather_orig(c));
         for (int k = 0; k < 3; ++k) srcs[k] = c->nw.alt + (size_t)(9 + k) * c->nR;
+    }
+    if (c->method == LJMD_METHOD_ALLPAIRS && c->pw.perm) { // device order -> caller's order through the stage
+        LJMD_TRY(ensure_stage(c));
+        for (int k = 0; k < 3; ++k)
+            if (dst[k]) LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_stage + (size_t)k * c->nR, srcs[k], bytes, cudaMemcpyDeviceToHost, c->stream));
+        LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < 3; ++k)
+            if (dst[k]) stage_out(c, dst[k], c->h_stage + (size_t)k * c->nR);
+        return LJMD_OK;
     }
     for (int k = 0; k < 3; ++k)
         if (dst[k]) LJMD_CUDA_CHECK(cudaMemcpyAsync(dst[k], srcs[k], bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -701,6 +785,8 @@ extern "C" int ljmd_ctx_device_ptrs(ljmd_ctx *c, double **pos0, double **pos1, d
     if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_device_ptrs(): ctx is NULL.");
     if (c->method == LJMD_METHOD_NLIST)
         return set_error(LJMD_ERR_UNSUPPORTED, "ljmd_ctx_device_ptrs(): the neighbour-list path keeps its state in cell-sorted order; use ljmd_ctx_download.");
+    if (c->method == LJMD_METHOD_ALLPAIRS && c->pw.sorted)
+        return set_error(LJMD_ERR_UNSUPPORTED, "ljmd_ctx_device_ptrs(): this all-pairs context keeps its state in a spatially sorted order; create it with LJMD_FLAG_NO_SORT or use ljmd_ctx_download.");
     if (pos0) *pos0 = c->rbuf[0];
     if (pos1) *pos1 = c->rbuf[1];
     if (vel) *vel = c->st.vx;
@@ -868,7 +954,7 @@ int compat_ctx(const ljmd_params *p, const char *who, ljmd_ctx **out)
         ljmd_ctx_destroy(g_compat); g_compat = nullptr;
     }
     if (!g_compat) {
-        ljmd_options o = {LJMD_METHOD_AUTO, -1, 1, 0};
+        ljmd_options o = {LJMD_METHOD_AUTO, -1, 1, LJMD_FLAG_NO_SORT}; // host arrays in/out every call: caller's order
         LJMD_TRY(ljmd_ctx_create(p, &o, &g_compat));
     } else if (memcmp(&g_compat->p, p, sizeof(*p)) != 0) {
         g_compat->p = *p;

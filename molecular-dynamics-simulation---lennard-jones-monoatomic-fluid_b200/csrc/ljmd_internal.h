@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "ljmd.h"
+#include "ljmd_debug.h"
 
 namespace ljmd {
 
@@ -80,6 +81,13 @@ struct PairWork {
     long long *dbg;       // optional per-warp timestamps of the independent-warp kernel (tuning)
     int4 *items;          // device work-item table
     double *fJ;           // [R][n_rows][3][n] j-side partial forces
+    // ---- variant 1, spatially sorted flavour (sparse cutoff, large N; lj_pairs_sorted_kernel) ----
+    bool sorted;          // the resident state is kept in a spatially sorted order (perm below)
+    int *perm;            // HOST: perm[slot] = original atom index (nullptr = identity)
+    long long steps_since_sort;
+    double *cbox;         // device [nchunks][6]: bounding box (lo xyz, hi xyz) of every 32-atom chunk
+    unsigned char *near;  // device [n_rows][nchunks]: 1 if the (row, chunk) tile wrote a j-side partial this step
+    unsigned *work;       // device [2]: dynamic work-item counter, finished-warp counter
     // ---- both ----
     int n_splits;    // variant 0: j splits; variant 1: max splits of any row
     int n_items;     // CTAs per replica (= scalar partials per replica)

@@ -79,6 +79,7 @@ struct FinArgs {
     int sym;                   // symmetric all-pairs kernel: also sum the j-side partials
     const double *fJ;          // [R][n_rows][3][n]
     int n_rows, tcta, nchunks;
+    const unsigned char *near; // sorted all-pairs kernel: [n_rows][nchunks], 1 = that j-side partial is valid this step
     const int *row_splits;     // [n_rows] i-side partials per row
     const int *perm;           // cells: fpart is in cell-sorted order; perm[i] = sorted slot of atom i
     int i_begin, i_end;        // atoms handled by this launch (the whole system unless sharded)
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
             const int P = nj + nsp;
 #pragma unroll 4
             for (int p = g; p < P; p += G) {
+                if (p < nj && a.near && !a.near[(size_t)p * a.nchunks + (i >> 5)]) continue; // row p did not touch this chunk
                 const double *src = (p < nj) ? fj + (size_t)p * 3 * n : fp + (size_t)(p - nj) * 3 * n;
                 fx += src[i];
                 fy += src[(size_t)n + i];
@@ -265,7 +267,7 @@ int launch_finalize(ljmd_ctx *c, int mode, int prev, int now, int out)
         a.spart = c->cw.spart;
         a.n_spart = c->cw.nblk_force;
         a.pair_weight = c->cw.pair_weight;
-        a.fJ = nullptr; a.n_rows = 0; a.tcta = 1; a.row_splits = nullptr; a.nchunks = 0;
+        a.fJ = nullptr; a.n_rows = 0; a.tcta = 1; a.row_splits = nullptr; a.nchunks = 0; a.near = nullptr;
     } else {
         a.fpart = c->pw.fpart;
         a.n_splits = c->pw.n_splits;
@@ -275,6 +277,7 @@ int launch_finalize(ljmd_ctx *c, int mode, int prev, int now, int out)
         a.tcta = c->pw.ri * 32 * c->pw.warps;
         a.row_splits = c->pw.row_splits;
         a.nchunks = (c->sc.n + 31) / 32;
+        a.near = c->pw.sorted ? c->pw.near : nullptr;
         a.spart = c->pw.spart;
         a.n_spart = c->pw.n_spart;
         a.pair_weight = (c->pw.variant == 0) ? 0.5 : 1.0;

@@ -154,7 +154,14 @@ class SlabRunner:
         import time
         while left > 0:
             t0 = time.perf_counter()
-            done, halted, obs = self.ctx.slab_run(min(self.chunk, left))
+            try:
+                done, halted, obs = self.ctx.slab_run(min(self.chunk, left))
+            except Exception:
+                try:  # tell the peers: their step kernels halt instead of spinning on this rank's flag
+                    self.ctx.slab_poison()
+                except Exception:
+                    pass
+                raise
             t1 = time.perf_counter()
             self.t_run += t1 - t0
             self.t_run_dev_ms += self.ctx.last_step_ms

@@ -72,3 +72,38 @@ def rel_err(got, want):
     if scale == 0.0:
         return float(np.max(np.abs(got - want)))
     return float(np.max(np.abs(got - want)) / scale)
+
+
+def force_scale(L, rc, x, y, z):
+    """Per-atom cancellation-aware scale of the acceleration: s_i = 24 * sum_j |g_ij| * |d_ij| over the
+    in-cutoff neighbours (g = (2 r^-12 - r^-6) / r^2, lj_potential_energy.f90:143-150), i.e. the sum of
+    the MAGNITUDES of the pair forces that add up to a_i.  "Forces within 1e-12 relative" is tested per
+    atom against this scale (|da_i| <= tol * s_i) next to the array-normalised rel_err(): an atom whose
+    pair forces nearly cancel must still be right to 1e-12 of what was summed.  Independent of the oracle:
+    scipy's periodic k-d tree finds the pairs."""
+    from scipy.spatial import cKDTree
+
+    pos = np.stack([x, y, z], axis=1)
+    pos = pos - L * np.floor(pos / L)
+    pos[pos >= L] -= L
+    pairs = cKDTree(pos, boxsize=L).query_pairs(rc, output_type="ndarray")
+    d = pos[pairs[:, 0]] - pos[pairs[:, 1]]
+    d -= L * np.rint(d / L)
+    r2 = (d * d).sum(axis=1)
+    ir2 = 1.0 / r2
+    ir6 = ir2 ** 3
+    mag = 24.0 * np.abs((2.0 * ir6 * ir6 - ir6) * ir2) * np.sqrt(r2)
+    s = np.zeros(len(x))
+    np.add.at(s, pairs[:, 0], mag)
+    np.add.at(s, pairs[:, 1], mag)
+    return s
+
+
+def assert_forces_close(got_xyz, want_xyz, scale, tol=1e-12, what="a"):
+    """Per-atom bound |got_i - want_i| <= tol * scale_i (see force_scale) on every component."""
+    for c, (g, w) in enumerate(zip(got_xyz, want_xyz)):
+        err = np.abs(np.asarray(g) - np.asarray(w))
+        bad = np.nonzero(err > tol * scale)[0]
+        assert len(bad) == 0, (f"{what}{'xyz'[c]}: {len(bad)} atoms outside {tol:g} of their pair-force scale; worst atom "
+                               f"{bad[np.argmax(err[bad] / scale[bad])]} err/scale "
+                               f"{np.max(err[bad] / scale[bad]):.3e}")

@@ -124,3 +124,20 @@ def test_cpp_host_links_and_fails_loudly_without_gpu(lj, tmp_path):
         assert run.returncode == 100 and "no CPU fallback" in run.stderr
     else:
         assert run.returncode == 0 and run.stdout.count("\n") >= 4
+
+
+def test_debug_exports_are_not_in_the_product_header(lj):
+    """Tuning / debug entry points live in csrc/ljmd_debug.h, not in include/ljmd.h."""
+    names = header_functions()
+    L = lj.load_library()
+    for name in lj.DEBUG_SYMBOLS:
+        assert name not in names and hasattr(L, name)
+
+
+def test_drop_in_pair_rejects_arrays_of_the_wrong_length(lj):
+    p = lj.init_params(500, 10.0, 1e-4, 4.9, 5)
+    s = lj.SimState(400)
+    with pytest.raises(ValueError):
+        lj.verlet_step(p, s)
+    with pytest.raises(ValueError):
+        lj.compute_lj_potential_energy(p, s)
