@@ -267,6 +267,10 @@ int ljmd_ctx_pair_counts(ljmd_ctx *ctx, int64_t *n_candidates, int64_t *n_in_cut
 /* Measured FP64 FMA throughput of the device the context lives on (register-resident DFMA
  * chains), in TFLOP/s; the roofline denominator for the all-pairs kernel. */
 int ljmd_measure_fp64_peak(int32_t device, double *tflops);
+/* The same chains launched back to back for `seconds` (0.05 .. 10) and timed over the second half: the
+ * throughput the FP64 pipe sustains once the clocks have settled under that load -- the denominator for
+ * a kernel timed inside a long run (ljmd_measure_fp64_peak is a burst right after idle). */
+int ljmd_measure_fp64_peak_sustained(int32_t device, double seconds, double *tflops);
 
 /* ==========================================================================================
  * Trajectory consumers: the heavy loops of the reference's analysis script

@@ -85,7 +85,7 @@ ABI_SYMBOLS = [
     "ljmd_ctx_compute_forces", "ljmd_ctx_step", "ljmd_ctx_step_series",
     "ljmd_ctx_kinetic_energy", "ljmd_ctx_method", "ljmd_ctx_cells_per_edge",
     "ljmd_ctx_launch_count", "ljmd_ctx_last_step_ms", "ljmd_ctx_force_timing", "ljmd_ctx_download_cells",
-    "ljmd_ctx_pair_counts", "ljmd_measure_fp64_peak",
+    "ljmd_ctx_pair_counts", "ljmd_measure_fp64_peak", "ljmd_measure_fp64_peak_sustained",
     "ljmd_ctx_set_stream", "ljmd_ctx_device_ptrs", "ljmd_ctx_set_shard", "ljmd_ctx_shard_begin",
     "ljmd_ctx_shard_step", "ljmd_ctx_shard_end", "ljmd_tail_corrections",
     "ljmd_ctx_nlist_info", "ljmd_ctx_download_nlist",
@@ -250,6 +250,13 @@ def tail_corrections(params: SimParams):
 def measure_fp64_peak(device: int = -1) -> float:
     t = C.c_double()
     _chk(load_library().ljmd_measure_fp64_peak(device, C.byref(t)))
+    return t.value
+
+
+def measure_fp64_peak_sustained(device: int = -1, seconds: float = 1.0) -> float:
+    """DFMA throughput sustained under `seconds` of back-to-back load (clocks settled), TFLOP/s."""
+    t = C.c_double()
+    _chk(load_library().ljmd_measure_fp64_peak_sustained(device, C.c_double(seconds), C.byref(t)))
     return t.value
 
 

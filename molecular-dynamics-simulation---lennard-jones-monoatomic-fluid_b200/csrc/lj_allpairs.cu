@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(512) lj_pairs_symw_kernel(SymArgs a, int n_ite
 struct SortedArgs {
     SymArgs s;
     const double *cbox;  // [nchunks][6] centre xyz, half width xyz of every j-chunk
-    unsigned char *near; // [n_rows][nchunks]
+    unsigned char *near; // [nchunks][n_rows]
     unsigned *work;      // [2] next item, finished warps
     int nchunks;
     double lim;          // L - rc - margin
@@ -693,7 +693,7 @@ __global__ void __launch_bounds__(512) lj_pairs_sorted_kernel(SortedArgs A, int 
                     fj[jg] = fjx; fj[(size_t)n + jg] = fjy; fj[2 * (size_t)n + jg] = fjz;
                 }
             }
-            if (lane == 0) A.near[(size_t)row * A.nchunks + chunk] = wrote ? 1 : 0;
+            if (lane == 0) A.near[(size_t)chunk * a.n_rows + row] = wrote ? 1 : 0;
             if (k + 1 < nchunks) {
                 sjw[buf ^ 1][0][lane] = px; sjw[buf ^ 1][1][lane] = py; sjw[buf ^ 1][2][lane] = pz;
             }
@@ -906,20 +906,25 @@ int pairwork_plan(ljmd_ctx *c)
             if (w.sorted) {
                 // 32-chunk items, then the rest of the row in pieces of <= 8 chunks: the items are handed
                 // out dynamically, longest first, so the short ones level the tail
-                // Pieces of 32 chunks from the diagonal outwards (the near-diagonal pieces carry the
-                // interaction work), and the far end of the row in ever smaller pieces: the items are handed out
-                // dynamically, longest first, so the small ones level the tail (a 128 x 32 tile is ~2 us of one
-                // warp when four warps share an FP64 pipe)
-                static const int tail_pieces[] = {16, 8, 8, 4, 4, 2, 2, 2, 1, 1};
+                // Pieces of at most 8 chunks, 4 next to the diagonal (the diagonal tiles take the general path and
+                // the spatially sorted order puts most of a row's interacting sub-tiles there), and the far end of
+                // the row in ever smaller pieces.  The items are handed out dynamically in order of estimated cost.
+                // Sizing rule (measured, profiles/r2_ncu_cfg3_sorted_v2/v3.txt): 2368 resident warps share 125 k
+                // tiles at N = 32k, 53 per warp; with 32-chunk pieces the SMs ran dry between 79 % and 100 % of
+                // the kernel time -- the largest piece has to be a small fraction of a warp's share.
+                static const int tail_pieces[] = {4, 4, 4, 2, 2, 2, 2, 1, 1, 1, 1};
                 int left = m, s = 0;
-                while (left > 48 + 32) { items.push_back(make_int4(r, c0, 32, s++)); c0 += 32; left -= 32; }
-                for (int q = 0; q < 10 && left > 48; ++q) { // left in (48, 80]: one more variable piece
-                    const int len = left - 48;
+                for (int q = 0; q < 2 && left > 24; ++q) {
+                    const int len = std::min(left - 24, 4);
                     items.push_back(make_int4(r, c0, len, s++));
                     c0 += len; left -= len;
-                    break;
                 }
-                for (int q = 0; q < 10 && left > 0; ++q) {
+                while (left > 24) {
+                    const int len = std::min(left - 24, 8);
+                    items.push_back(make_int4(r, c0, len, s++));
+                    c0 += len; left -= len;
+                }
+                for (int q = 0; q < 11 && left > 0; ++q) {
                     const int len = std::min(left, tail_pieces[q]);
                     items.push_back(make_int4(r, c0, len, s++));
                     c0 += len; left -= len;
@@ -945,7 +950,22 @@ int pairwork_plan(ljmd_ctx *c)
         LJMD_CUDA_CHECK(cudaMalloc(&w.row_splits, sizeof(int) * w.n_rows));
         LJMD_CUDA_CHECK(cudaMemcpy(w.row_splits, row_splits.data(), sizeof(int) * w.n_rows, cudaMemcpyHostToDevice));
         // heavy items first: full-length runs before the short tails (stable => deterministic)
-        std::stable_sort(items.begin(), items.end(), [](const int4 &x, const int4 &y) { return x.z > y.z; });
+        if (w.sorted) {
+            // estimated cost in far-tile units: chunks at offset d from the row's diagonal weigh 5 (d < 4: general
+            // path), 2 (d < 32), 1.5 (d < 128), 1 (beyond) -- the measured density of interacting sub-tiles
+            const int cpr = tcta / 32; // chunks per row of i-atoms
+            auto cost = [cpr](const int4 &it) {
+                double c = 0.0;
+                for (int k = 0; k < it.z; ++k) {
+                    const int d = it.y + k - it.x * cpr;
+                    c += d < 4 ? 5.0 : d < 32 ? 2.0 : d < 128 ? 1.5 : 1.0;
+                }
+                return c;
+            };
+            std::stable_sort(items.begin(), items.end(), [&](const int4 &x, const int4 &y) { return cost(x) > cost(y); });
+        } else {
+            std::stable_sort(items.begin(), items.end(), [](const int4 &x, const int4 &y) { return x.z > y.z; });
+        }
         w.n_items = (int)items.size();
         w.n_splits = max_splits;
         w.n_ctas = w.n_items;

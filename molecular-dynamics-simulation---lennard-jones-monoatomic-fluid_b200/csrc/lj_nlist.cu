@@ -637,7 +637,7 @@ __device__ __forceinline__ void nl_st_release_sys(int *p, int v)
 // Resident threads per SM the register allocation is sized for (build-time knobs for A/B libraries,
 // `make variant`): PIPE 512, TPA > 1 640, sharded / force-only 768, plain step 1024.
 #ifndef LJMD_NL_THREADS_SH
-#define LJMD_NL_THREADS_SH 768
+#define LJMD_NL_THREADS_SH 1024 // 8 CTAs per SM: the 1050 CTAs of the fullest rank of an 8-GPU run at N = 2^20 are ONE wave
 #endif
 #ifndef LJMD_NL_PUBLISH_IN_KERNEL
 #define LJMD_NL_PUBLISH_IN_KERNEL 0 // 1: the last CTA of a sharded step publishes the flags itself
@@ -656,6 +656,8 @@ nl_step_kernel(NlArgs a)
     __shared__ double scratch[NL_NS * (NL_BS / 32)];
     __shared__ bool is_last;
     __shared__ int s_viol;
+    __shared__ int s_flag;
+    (void)s_flag;
     constexpr int APB = NL_BS / TPA; // atoms per CTA
     const int n = a.sc.n;
     const int sub = threadIdx.x % TPA;
@@ -670,35 +672,41 @@ nl_step_kernel(NlArgs a)
         // thread 0 left, the others passed the barrier, read a never-written s_viol and advanced their
         // atoms by a step nobody else took.  That is the rare "wrong velocities in a block of CTAs
         // around a rebuild" of DESIGN.md section 6.)
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 32) { // warp 0 decides; lanes 0 .. world-1 wait for one rank's flag each, in parallel
+            const int lane = threadIdx.x;
             int viol = 0;
-            const int layer = a.nc * a.nc;
-            const int owned = a.cell_start[a.xhi * layer] - a.cell_start[a.xlo * layer];
-            if (a.ctl->halted || a.ctl->steps_left <= 0 || a.ctl->overflow != 0) {
-                viol = 2; // nothing to do in this launch (a list overflow freezes the state at the last valid step)
-            } else if ((int)blockIdx.x >= (owned + APB - 1) / APB) {
-                viol = 2; // CTA beyond the owned range (the grid is sized with slack): must not wait for flags
-            } else if (seq > 0) {
+            if (lane == 0) {
+                const int layer = a.nc * a.nc;
+                const int owned = a.cell_start[a.xhi * layer] - a.cell_start[a.xlo * layer];
+                if (a.ctl->halted || a.ctl->steps_left <= 0 || a.ctl->overflow != 0)
+                    viol = 2; // nothing to do in this launch (a list overflow freezes the state at the last valid step)
+                else if ((int)blockIdx.x >= (owned + APB - 1) / APB)
+                    viol = 2; // CTA beyond the owned range (the grid is sized with slack): must not wait for flags
+            }
+            viol = __shfl_sync(0xffffffffu, viol, 0);
+            if (viol == 0 && seq > 0) {
                 // Wait for every rank's flag of step seq, but never forever: a peer that died, stopped
                 // launching after an error or was given another step count would otherwise leave this GPU
                 // spinning until a reset.  On expiry the run halts with NL_ERR_FLAG_TIMEOUT (the host
                 // reports LJMD_ERR_CUDA); a failing rank also publishes a poison flag (NL_FLAG_POISON).
-                const int *f = a.flags + (seq & 1) * LJMD_MAX_RANKS;
-                const unsigned long long t0 = nl_globaltimer();
-                for (int q = 0; q < a.world && viol != 2; ++q) {
-                    int v;
-                    while (((v = nl_ld_acquire_sys(f + q)) >> 1) < seq) {
+                int v = seq << 1;
+                bool late = false;
+                if (lane < a.world) {
+                    const int *f = a.flags + (seq & 1) * LJMD_MAX_RANKS + lane;
+                    const unsigned long long t0 = nl_globaltimer();
+                    while (((v = nl_ld_acquire_sys(f)) >> 1) < seq) {
                         __nanosleep(40);
-                        if (nl_globaltimer() - t0 > a.spin_budget_ns) { viol = 2; break; }
+                        if (nl_globaltimer() - t0 > a.spin_budget_ns) { late = true; break; }
                     }
-                    if (viol != 2) viol |= v & 1;
                 }
-                if (viol == 2) { // timed out: freeze this rank (every CTA of this and later launches leaves at once)
-                    atomicMax(&a.ctl->overflow, NL_ERR_FLAG_TIMEOUT);
-                    a.ctl->halted = 1;
+                if (__any_sync(0xffffffffu, late)) { // timed out: freeze this rank (every CTA of this and later launches leaves at once)
+                    if (lane == 0) { atomicMax(&a.ctl->overflow, NL_ERR_FLAG_TIMEOUT); a.ctl->halted = 1; }
+                    viol = 2;
+                } else if (__any_sync(0xffffffffu, (v & 1) != 0)) {
+                    viol = 1;
                 }
             }
-            s_viol = viol;
+            if (lane == 0) s_viol = viol;
         }
         __syncthreads();
         if (s_viol & 2) return;
@@ -759,6 +767,8 @@ nl_step_kernel(NlArgs a)
 
     double s[NL_NS] = {s12, s6, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}; // every lane contributes its own share of the pair sums
     double d2 = 0.0;
+    bool pushed = false; // this thread stored a halo position into a peer rank's buffer
+    (void)pushed;
     if (valid && sub == 0) {
         const size_t ix = i, iy = ix + n, iz = iy + n;
         const double axn = 24.0 * fx, ayn = 24.0 * fy, azn = 24.0 * fz; // lj_potential_energy.f90:189-191
@@ -787,11 +797,11 @@ nl_step_kernel(NlArgs a)
                 const size_t off = (size_t)cur * n + i;
                 if (i < a.cell_start[(a.xlo + 1) * layer]) {
                     const int left = (a.rank + a.world - 1) % a.world;
-                    if (left != a.rank) nl_st_pos(a.peer_p4[left] + off, xn, yn, zn);
+                    if (left != a.rank) { nl_st_pos(a.peer_p4[left] + off, xn, yn, zn); pushed = true; }
                 }
                 if (i >= a.cell_start[(a.xhi - 1) * layer]) {
                     const int right = (a.rank + 1) % a.world;
-                    if (right != a.rank) nl_st_pos(a.peer_p4[right] + off, xn, yn, zn);
+                    if (right != a.rank) { nl_st_pos(a.peer_p4[right] + off, xn, yn, zn); pushed = true; }
                 }
             }
             d2 = nl_disp2(a, i, xn, yn, zn);
@@ -802,8 +812,12 @@ nl_step_kernel(NlArgs a)
     }
     block_sum<NL_NS>(s, scratch);
     if (MODE == 1) nl_block_max(d2, scratch, a.ctl);
-    if (SH) { // EVERY thread's remote halo stores are performed system-wide before thread 0 takes the ticket
-        __threadfence_system();
+    if (SH) {
+        // Every thread that stored into a peer's buffer makes those stores visible system-wide BEFORE it arrives at
+        // the barrier below; thread 0 takes the ticket after the barrier, and the flag is published (release, system
+        // scope) only after all tickets: a peer that acquires the flag sees every halo position.  Threads (and whole
+        // CTAs: all but the two boundary layers) that pushed nothing skip the fence -- MEMBAR.SYS is not free.
+        if (pushed) __threadfence_system();
         __syncthreads();
     }
     if (threadIdx.x == 0) {
@@ -853,12 +867,7 @@ nl_step_kernel(NlArgs a)
                 const int flag_val = ((seq + 1) << 1) | (m > a.half_skin2 ? 1 : 0);
                 a.ctl->pending_flag = flag_val;
 #if LJMD_NL_PUBLISH_IN_KERNEL
-                // A/B build (`make variant DEFS=-DLJMD_NL_PUBLISH_IN_KERNEL=1`): publish from here and
-                // save one launch per step.  Every CTA fenced its halo stores system-wide before taking
-                // its ticket and this CTA saw all tickets, so the release stores below order them.
-                __threadfence_system();
-                for (int q = 0; q < a.world; ++q)
-                    nl_st_release_sys(a.peer_flags[q] + ((seq + 1) & 1) * LJMD_MAX_RANKS + a.rank, flag_val);
+                s_flag = flag_val; // published below by one lane per peer
 #endif
                 a.ctl->seq = seq + 1;
                 a.ctl->steps_left -= 1;
@@ -867,6 +876,17 @@ nl_step_kernel(NlArgs a)
         }
         a.ctl->ticket_step = 0;
     }
+#if LJMD_NL_PUBLISH_IN_KERNEL
+    if (SH && MODE == 1) {
+        // Publish "step seq+1 done (+ skin violated)" from here and save one launch per step.  Every thread that
+        // pushed halo positions fenced them system-wide before its CTA took the ticket and this CTA saw all
+        // tickets, so the release stores below order them.  One lane per peer: world release stores issued by
+        // one thread would queue up behind each other's round trips.
+        __syncthreads();
+        if ((int)threadIdx.x < a.world)
+            nl_st_release_sys(a.peer_flags[threadIdx.x] + ((seq + 1) & 1) * LJMD_MAX_RANKS + a.rank, s_flag);
+    }
+#endif
 }
 
 // First step of a run: rb[1-cur] = wrap(drift(rb[cur], v, a)) (verlet.f90:58-63) + skin check.
@@ -985,13 +1005,14 @@ __global__ void __launch_bounds__(256) nl_checksum_kernel(NlArgs a, unsigned lon
 // alternately, where a peer's next launch cannot run while this one waits.
 __global__ void nl_publish_kernel(NlArgs a)
 {
-    if (threadIdx.x != 0) return;
+    // one lane per peer: the system-scope release stores of a single thread would queue up behind each other
+    // (each waits for the round trip of the one before), world of them in parallel cost one round trip
+    if ((int)threadIdx.x >= a.world) return;
     const int seq = a.ctl->seq;
     if (seq <= 0 || a.ctl->halted) return;
     const int val = a.ctl->pending_flag;
     const int slot = (seq & 1) * LJMD_MAX_RANKS + a.rank;
-    __threadfence_system();
-    for (int q = 0; q < a.world; ++q) nl_st_release_sys(a.peer_flags[q] + slot, val);
+    nl_st_release_sys(a.peer_flags[threadIdx.x] + slot, val);
 }
 
 // Debug: checksums keyed by the ORIGINAL atom index: invariant under a correct permutation.
@@ -1102,7 +1123,8 @@ static NlArgs make_args(ljmd_ctx *c, int eval_sel)
     a.flags = w.flags;
     a.dbg_exec = w.dbg_exec;
     {
-        static const double budget_s = getenv("LJMD_SLAB_SPIN_TIMEOUT_S") ? atof(getenv("LJMD_SLAB_SPIN_TIMEOUT_S")) : 10.0;
+        const char *e = w.sh_on ? getenv("LJMD_SLAB_SPIN_TIMEOUT_S") : nullptr;
+        const double budget_s = e ? atof(e) : 10.0;
         a.spin_budget_ns = (unsigned long long)((budget_s > 0.0 ? budget_s : 10.0) * 1e9);
     }
     if (w.sh_on) { a.sc.tail_u = 0.0; a.sc.tail_du = 0.0; a.sc.tail_ddu = 0.0; } // added once, after the cross-rank reduction
@@ -1540,7 +1562,9 @@ extern "C" int ljmd_ctx_slab_attach(ljmd_ctx *c, int32_t rank, int32_t world, co
         slab_layers(w.nc, rank, world, &w.xlo, &w.xhi);
         // CTAs of the step kernel: room for 30 % more atoms than the mean slab (+ one layer's worth)
         const double mean = (double)c->sc.n * (w.xhi - w.xlo) / w.nc;
-        w.pipe = (mean <= 262144.0) ? 1 : 0;
+        // sharded runs: the plain walk at 8 CTAs per SM (the pipelined variant holds 4 CTAs per SM: two waves for an
+        // 8-GPU slab of N = 2^20, and it measured 14 % slower at 2 GPUs, profiles/r2_slab_variants_n2.txt)
+        w.pipe = 0;
         if (const char *e = getenv("LJMD_NL_PIPE")) w.pipe = atoi(e) != 0;
         const int apb = NL_BS / w.tpa;
         w.own_blocks = (int)((1.3 * mean + 4096.0) / apb) + 1;

@@ -520,7 +520,7 @@ extern "C" int ljmd_ctx_create(const ljmd_params *params, const ljmd_options *op
     // small systems: 8 thread groups share each atom's partial sum (many partials, few atoms)
     c->fw.groups = (method == LJMD_METHOD_ALLPAIRS && params->n <= 65536) ? 8 : 1;
     c->fw.nblk = (params->n + (256 / c->fw.groups) - 1) / (256 / c->fw.groups);
-    CREATE_CHECK(cudaMalloc(&c->fw.kpart, sizeof(double) * 3 * (size_t)c->fw.nblk * c->R));
+    CREATE_CHECK(cudaMalloc(&c->fw.kpart, sizeof(double) * 6 * (size_t)c->fw.nblk * c->R)); // per CTA: 3 E_kin + 3 pair-sum partials
     CREATE_CHECK(cudaMalloc(&c->fw.counter, sizeof(unsigned) * (c->R + 1)));
     CREATE_CHECK(cudaMemsetAsync(c->fw.counter, 0, sizeof(unsigned) * (c->R + 1), c->stream));
     CREATE_CHECK(cudaMalloc(&c->fw.ctl, sizeof(StepCtl)));
@@ -932,6 +932,15 @@ extern "C" int ljmd_measure_fp64_peak(int32_t device, double *tflops)
     if (ljmd_device_count() == 0)
         return set_error(LJMD_ERR_CUDA, "ljmd_measure_fp64_peak(): no CUDA device available.");
     return measure_fp64_peak(device, tflops);
+}
+
+extern "C" int ljmd_measure_fp64_peak_sustained(int32_t device, double seconds, double *tflops)
+{
+    clear_error();
+    if (!tflops) return set_error(LJMD_ERR_NULL, "ljmd_measure_fp64_peak_sustained(): tflops is NULL.");
+    if (ljmd_device_count() == 0)
+        return set_error(LJMD_ERR_CUDA, "ljmd_measure_fp64_peak_sustained(): no CUDA device available.");
+    return measure_fp64_peak_sustained(device, seconds, tflops);
 }
 
 // ==========================================================================================

@@ -86,7 +86,7 @@ struct PairWork {
     int *perm;            // HOST: perm[slot] = original atom index (nullptr = identity)
     long long steps_since_sort;
     double *cbox;         // device [nchunks][6]: bounding box (lo xyz, hi xyz) of every 32-atom chunk
-    unsigned char *near;  // device [n_rows][nchunks]: 1 if the (row, chunk) tile wrote a j-side partial this step
+    unsigned char *near;  // device [nchunks][n_rows]: 1 if the (row, chunk) tile wrote a j-side partial this step
     unsigned *work;       // device [2]: dynamic work-item counter, finished-warp counter
     // ---- both ----
     int n_splits;    // variant 0: j splits; variant 1: max splits of any row
@@ -99,7 +99,7 @@ struct FinalizeWork {
     int block;          // threads per CTA
     int groups;         // thread groups sharing one atom's partial sum (1 or 8)
     int nblk;           // CTAs per replica
-    double *kpart;      // [R][nblk][3] partial sums of vx^2, vy^2, vz^2
+    double *kpart;      // [R][nblk][6] per-CTA partial sums: vx^2, vy^2, vz^2 and a slice of the force kernel's scalar partials
     unsigned *counter;  // [R] last-block tickets
     double *obs;        // [R][4] observables of the last step: epot, ekin, d_epot, dd_epot
     StepCtl *ctl;       // device control block
@@ -239,6 +239,7 @@ int launch_drift(ljmd_ctx *c, int from, int to);
 int launch_finalize(ljmd_ctx *c, int mode, int prev, int now, int out);
 int launch_ekin_driver(ljmd_ctx *c, double *d_out);
 int measure_fp64_peak(int device, double *tflops);
+int measure_fp64_peak_sustained(int device, double seconds, double *tflops);
 
 // ---- lj_allpairs.cu ----------------------------------------------------------------------
 int pairwork_plan(ljmd_ctx *c);

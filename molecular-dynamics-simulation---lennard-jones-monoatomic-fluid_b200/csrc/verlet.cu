@@ -79,7 +79,7 @@ struct FinArgs {
     int sym;                   // symmetric all-pairs kernel: also sum the j-side partials
     const double *fJ;          // [R][n_rows][3][n]
     int n_rows, tcta, nchunks;
-    const unsigned char *near; // sorted all-pairs kernel: [n_rows][nchunks], 1 = that j-side partial is valid this step
+    const unsigned char *near; // sorted all-pairs kernel: [nchunks][n_rows], 1 = that j-side partial is valid this step
     const int *row_splits;     // [n_rows] i-side partials per row
     const int *perm;           // cells: fpart is in cell-sorted order; perm[i] = sorted slot of atom i
     int i_begin, i_end;        // atoms handled by this launch (the whole system unless sharded)
@@ -124,13 +124,46 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
             const double *fj = a.sym ? a.fJ + (size_t)rep * a.n_rows * 3 * n : nullptr;
             const double *fp = a.fpart + (size_t)rep * a.n_splits * 3 * n;
             const int P = nj + nsp;
+            if (!a.near) {
 #pragma unroll 4
-            for (int p = g; p < P; p += G) {
-                if (p < nj && a.near && !a.near[(size_t)p * a.nchunks + (i >> 5)]) continue; // row p did not touch this chunk
-                const double *src = (p < nj) ? fj + (size_t)p * 3 * n : fp + (size_t)(p - nj) * 3 * n;
-                fx += src[i];
-                fy += src[(size_t)n + i];
-                fz += src[2 * (size_t)n + i];
+                for (int p = g; p < P; p += G) {
+                    const double *src = (p < nj) ? fj + (size_t)p * 3 * n : fp + (size_t)(p - nj) * 3 * n;
+                    fx += src[i];
+                    fy += src[(size_t)n + i];
+                    fz += src[2 * (size_t)n + i];
+                }
+            } else { // i-side partials of the sorted kernel (the flagged j-side partials are added below)
+#pragma unroll 4
+                for (int p = g; p < nsp; p += G) {
+                    const double *src = fp + (size_t)p * 3 * n;
+                    fx += src[i];
+                    fy += src[(size_t)n + i];
+                    fz += src[2 * (size_t)n + i];
+                }
+            }
+        }
+    }
+    if (G == 8 && a.near) {
+        // Sorted all-pairs kernel: only the (row, chunk) tiles that held an in-cutoff pair wrote a j-side
+        // partial; near[chunk][row] says which.  APB = 32: this CTA is ONE chunk and warp g = group g.  The
+        // warp reads the flags of 32 rows with one coalesced load, and walks the set bits in ascending row
+        // order (fixed order => bit-reproducible); warp g takes the row batches g, g+8, ...
+        const int first = a.i_begin + blockIdx.x * APB;  // first atom of the chunk (i_begin is a multiple of 32 here)
+        const int chunk = first >> 5, rowmax = first / a.tcta;
+        const double *fj = a.fJ + (size_t)rep * a.n_rows * 3 * n;
+        const unsigned char *flags = a.near + (size_t)chunk * a.n_rows;
+        for (int b = g; b * 32 <= rowmax; b += G) {
+            const int r = b * 32 + la;
+            unsigned m = __ballot_sync(0xffffffffu, r <= rowmax && flags[r] != 0);
+            while (m) {
+                const int rr = b * 32 + __ffs(m) - 1;
+                m &= m - 1;
+                if (i < i_end) {
+                    const double *src = fj + (size_t)rr * 3 * n;
+                    fx += src[i];
+                    fy += src[(size_t)n + i];
+                    fz += src[2 * (size_t)n + i];
+                }
             }
         }
     }
@@ -177,9 +210,25 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
         k[0] = vx * vx; k[1] = vy * vy; k[2] = vz * vz; // verlet.f90:93-95
     }
     block_sum<3>(k, scratch);
+    // Scalar partials of the force kernel, level 1: CTA b adds the slice [b*S, (b+1)*S) of them in index order
+    // (fixed shape => bit-reproducible).  One CTA walking all of them alone was the tail of this kernel: 19 k
+    // work items at N = 32k cost it 60 us.
+    double sl[3] = {0.0, 0.0, 0.0};
+    {
+        const int S = (a.n_spart + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int b0 = blockIdx.x * S, b1 = min(a.n_spart, b0 + S);
+        const double *sp = a.spart + (size_t)rep * a.n_spart * 3;
+        for (int b = b0 + threadIdx.x; b < b1; b += blockDim.x) {
+            sl[0] += sp[3 * b + 0];
+            sl[1] += sp[3 * b + 1];
+            sl[2] += sp[3 * b + 2];
+        }
+    }
+    block_sum<3>(sl, scratch);
     if (threadIdx.x == 0) {
-        double *kp = a.kpart + ((size_t)rep * gridDim.x + blockIdx.x) * 3;
+        double *kp = a.kpart + ((size_t)rep * gridDim.x + blockIdx.x) * 6;
         kp[0] = k[0]; kp[1] = k[1]; kp[2] = k[2];
+        kp[3] = sl[0]; kp[4] = sl[1]; kp[5] = sl[2];
         __threadfence();
         const unsigned ticket = atomicAdd(&a.counter[rep], 1u);
         is_last = (ticket == gridDim.x - 1);
@@ -188,22 +237,19 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
     if (!is_last) return;
     __threadfence();
 
-    // Fixed-order reduction of all scalar partials of this replica.
+    // Level 2: fixed-order reduction of the per-CTA partials of this replica.
     double s[3] = {0.0, 0.0, 0.0};
-    const double *sp = a.spart + (size_t)rep * a.n_spart * 3;
-    for (int b = threadIdx.x; b < a.n_spart; b += blockDim.x) {
-        s[0] += __ldcg(sp + 3 * b + 0);
-        s[1] += __ldcg(sp + 3 * b + 1);
-        s[2] += __ldcg(sp + 3 * b + 2);
+    double kk[3] = {0.0, 0.0, 0.0};
+    const double *kp = a.kpart + (size_t)rep * gridDim.x * 6;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+        kk[0] += __ldcg(kp + 6 * b + 0);
+        kk[1] += __ldcg(kp + 6 * b + 1);
+        kk[2] += __ldcg(kp + 6 * b + 2);
+        s[0] += __ldcg(kp + 6 * b + 3);
+        s[1] += __ldcg(kp + 6 * b + 4);
+        s[2] += __ldcg(kp + 6 * b + 5);
     }
     block_sum<3>(s, scratch);
-    double kk[3] = {0.0, 0.0, 0.0};
-    const double *kp = a.kpart + (size_t)rep * gridDim.x * 3;
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
-        kk[0] += __ldcg(kp + 3 * b + 0);
-        kk[1] += __ldcg(kp + 3 * b + 1);
-        kk[2] += __ldcg(kp + 3 * b + 2);
-    }
     block_sum<3>(kk, scratch);
     if (threadIdx.x == 0) {
         const double w = a.pair_weight;
@@ -338,6 +384,43 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
     }
     const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
     if (s == 123.456) out[0] = s; // never true; keeps the chains alive
+}
+
+// The same DFMA chains launched back to back for `seconds` and timed over the second half: the
+// throughput the FP64 pipe SUSTAINS once the clocks have settled under that load -- the denominator
+// for a kernel timed inside a long run (a short burst right after idle runs at the maximum clock).
+int measure_fp64_peak_sustained(int device, double seconds, double *tflops)
+{
+    int prev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+    if (device >= 0) LJMD_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    int dev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&dev));
+    LJMD_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    double *d = nullptr;
+    LJMD_CUDA_CHECK(cudaMalloc(&d, 8));
+    cudaEvent_t e0, e1;
+    LJMD_CUDA_CHECK(cudaEventCreate(&e0));
+    LJMD_CUDA_CHECK(cudaEventCreate(&e1));
+    const int iters = 2048, block = 256, grid = prop.multiProcessorCount * 8;
+    const double flops = 2.0 * 64.0 * iters * (double)block * grid; // per launch, ~0.37 ms at the nominal peak
+    if (!(seconds > 0.05)) seconds = 0.05;
+    if (seconds > 10.0) seconds = 10.0;
+    const int nl = (int)(seconds * 0.5 / 0.00037) + 1; // launches per half
+    for (int k = 0; k < nl; ++k) dfma_peak_kernel<<<grid, block>>>(d, iters, 0.999999, 1e-7);
+    LJMD_CUDA_CHECK(cudaEventRecord(e0));
+    for (int k = 0; k < nl; ++k) dfma_peak_kernel<<<grid, block>>>(d, iters, 0.999999, 1e-7);
+    LJMD_CUDA_CHECK(cudaEventRecord(e1));
+    LJMD_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    LJMD_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (device >= 0) cudaSetDevice(prev);
+    *tflops = flops * nl / (ms * 1e-3) / 1e12;
+    return LJMD_OK;
 }
 
 int measure_fp64_peak(int device, double *tflops)

@@ -74,7 +74,7 @@ def rel_err(got, want):
     return float(np.max(np.abs(got - want)) / scale)
 
 
-def force_scale(L, rc, x, y, z):
+def force_scale(L, rc, x, y, z, return_sums=False):
     """Per-atom cancellation-aware scale of the acceleration: s_i = 24 * sum_j |g_ij| * |d_ij| over the
     in-cutoff neighbours (g = (2 r^-12 - r^-6) / r^2, lj_potential_energy.f90:143-150), i.e. the sum of
     the MAGNITUDES of the pair forces that add up to a_i.  "Forces within 1e-12 relative" is tested per
@@ -96,7 +96,18 @@ def force_scale(L, rc, x, y, z):
     s = np.zeros(len(x))
     np.add.at(s, pairs[:, 0], mag)
     np.add.at(s, pairs[:, 1], mag)
+    if return_sums:
+        return s, float(np.sum(ir6 * ir6)), float(np.sum(ir6))
     return s
+
+
+def scalar_scales(s12, s6, tails):
+    """Cancellation-aware scales of (epot, d_epot, dd_epot): the sums of the MAGNITUDES of what is added up,
+    4 (S12 + S6), 24 (2 S12 + S6), 24 (26 S12 + 7 S6) plus |tail| (lj_potential_energy.f90:140,143,178,
+    188-223).  d_epot = 24 (-2 S12 + S6) + tail passes through zero near the zero-pressure density, where a
+    bound relative to d_epot itself would ask for more digits than a 1e6-term FP64 sum has in ANY order."""
+    return (4.0 * (s12 + s6) + abs(tails[0]), 24.0 * (2.0 * s12 + s6) + abs(tails[1]),
+            24.0 * (26.0 * s12 + 7.0 * s6) + abs(tails[2]))
 
 
 def assert_forces_close(got_xyz, want_xyz, scale, tol=1e-12, what="a"):

@@ -345,3 +345,50 @@ def test_nlist_slab_two_ranks_emulated(lj, O):
         finally:
             for c in ctxs:
                 c.close()
+
+
+@pytest.mark.timeout(120, method="thread")
+def test_nlist_slab_flag_wait_is_bounded_and_poison_halts(lj, O):
+    """A peer that never publishes its per-step flag must not leave the GPU spinning: the wait ends after
+    LJMD_SLAB_SPIN_TIMEOUT_S with LJMD_ERR_CUDA and the state frozen at the last completed step; a peer that
+    publishes the poison flag makes the waiting rank halt at once (no error, halted = 1)."""
+    p_o, st = make_config(O, "cfg3")
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    import time
+    with _env(LJMD_SLAB_SPIN_TIMEOUT_S=1.5):
+        ctxs = [lj.Context(p, method=lj.METHOD_NLIST) for _ in range(2)]
+        try:
+            for c in ctxs:
+                c.upload(_state(lj, st))
+                c.compute_forces()
+            raw = [c.slab_export()[1] for c in ctxs]
+            for r, c in enumerate(ctxs):
+                c.slab_attach(r, 2, raw_ptrs=raw)
+                c.slab_drift()
+                c.slab_rebuild()
+            # step 1 needs no flag; step 2 waits for rank 1's flag of step 1, which never comes
+            t0 = time.perf_counter()
+            with pytest.raises(lj.LjmdError) as ei:
+                ctxs[0].slab_run(2)
+            waited = time.perf_counter() - t0
+            assert ei.value.code == 100 and "flag" in ei.value.message
+            assert 1.0 < waited < 30.0
+        finally:
+            for c in ctxs:
+                c.close()
+        ctxs = [lj.Context(p, method=lj.METHOD_NLIST) for _ in range(2)]
+        try:
+            for c in ctxs:
+                c.upload(_state(lj, st))
+                c.compute_forces()
+            raw = [c.slab_export()[1] for c in ctxs]
+            for r, c in enumerate(ctxs):
+                c.slab_attach(r, 2, raw_ptrs=raw)
+                c.slab_drift()
+                c.slab_rebuild()
+            ctxs[1].slab_poison()           # rank 1 "failed"
+            done, halted, _ = ctxs[0].slab_run(3)
+            assert done == 1 and halted     # step 1 ran (it waits for nothing), step 2 saw the poison and halted
+        finally:
+            for c in ctxs:
+                c.close()
