@@ -495,6 +495,65 @@ def run_slabs(args, w, lj, mg, dist, rank, world, local, n, arrs, p):
     dist.destroy_process_group()
 
 
+def run_ensemble_bench(args, w, lj, dist, rank, world, local):
+    """BASELINE.json configs[4]: an ensemble of independent N = 500 replicas (run_many_md_simuations intent,
+    run_many_md.f90:57-82), 64 per GPU, replica r (global index) started like md_initial_config_program with the
+    velocity seed -(12345 + r), batched in ONE context per GPU, sampled every 100 steps, no
+    communication during the run, ONE final NCCL reduction of the per-replica thermodynamic coefficients
+    (thermodynamic_coefs.f90:87-205) to the ensemble mean / population std.  A "step" is one velocity-Verlet
+    step of every replica; the timed region is the whole run_ensemble call (sampling + the final reduction
+    included) after a warm-up call of the same shape."""
+    import importlib
+    ic = importlib.import_module(lj.__name__ + ".initial_config")
+    ob = importlib.import_module(lj.__name__ + ".observables")
+    R = int(w.get("replicas", 64))
+    n = 4 * w["k"] ** 3
+    p = lj.init_params(n, w["L"], w["dt"], w["rc"], w["k"])
+    states = [ic.initial_config(lj, p, seed=-(12345 + rank * R + r), target_total_energy=-555.0 * n / 500.0)[0] for r in range(R)]
+    lj.compat_release()
+    interval = 100
+    steps = max(interval, (args.steps // interval) * interval)
+    warm = max(interval, (args.warmup // interval) * interval)
+    ob.run_ensemble(lj, p, states, warm, interval, 0, device=local)  # warm-up: kernels, graphs, NCCL channels
+    if dist is not None:
+        import torch
+        torch.cuda.synchronize()
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0 = time.perf_counter()
+    out = ob.run_ensemble(lj, p, states, steps, interval, 0, device=local)
+    el = time.perf_counter() - t0
+    clocks = sampler.finish()
+    if dist is not None:
+        import torch
+        t = torch.tensor([el], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        el = float(t.item())
+    if rank == 0:
+        line = {
+            "metric": "atom_steps_per_s", "value": n * R * world * steps / el, "unit": "atom-steps/s",
+            "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * el / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_of(args.workload, world),
+            "roofline": None, "cpu_baseline": None, "e2e": None, "clocks": clocks,
+            "gpu_launches": int(2 * steps * world + world),
+            "timing": "host wall clock around observables.run_ensemble (max over ranks): H2D of the replicas, the steps, "
+                      "the per-sample D2H of 4 observables per replica and the final reduction are all inside",
+            "ensemble": {"n_replicas": out["n_replicas"], "n_samples": out["n_samples"],
+                         "reduction": "multi_gpu.ensemble_reduce: one NCCL all-gather of (sum, sum of squares, count) per "
+                                      "coefficient, added in rank order" if dist is not None else "single rank",
+                         "mean": {k: out["mean"][k] for k in ("temperature", "pressure", "Ca_v", "Ce_v", "gamma", "K_S", "alpha_E1", "alpha_E2")
+                                  if k in out["mean"]},
+                         "std": {k: out["std"][k] for k in ("temperature", "pressure", "Ca_v", "Ce_v", "gamma", "K_S", "alpha_E1", "alpha_E2")
+                                 if k in out["std"]}},
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_sharded(args, w, lj, dist, rank, world, local, n, arrs, p):
     """Strong scaling of ONE large system (cell list) over the ranks: i-particle-range sharding,
     NCCL all-gather of the positions every step, observables reduced in rank order."""
@@ -608,6 +667,8 @@ def main():
     if lj.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
 
+    if args.workload == "cfg5_ensemble" and not os.environ.get("LJMD_BENCH_SYNTHETIC_REPLICAS"):
+        return run_ensemble_bench(args, w, lj, dist, rank, world, local)
     sharded = (world > 1 or os.environ.get("LJMD_BENCH_FORCE_SLABS")) and shards(w)
     if sharded and dist is None:  # diagnostic: the sharded code path with a single rank
         import torch

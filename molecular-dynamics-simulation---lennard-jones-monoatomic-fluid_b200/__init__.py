@@ -96,7 +96,7 @@ ABI_SYMBOLS = [
 ]
 # Tuning / debug exports declared in csrc/ljmd_debug.h, not in the product header.
 DEBUG_SYMBOLS = ["ljmd_bench_chunk_cycles", "ljmd_ctx_debug_warp_times", "ljmd_ctx_debug_checksum",
-                 "ljmd_ctx_slab_publish"]
+                 "ljmd_ctx_slab_publish", "ljmd_ctx_debug_slab_timeline"]
 MAX_RANKS = 8
 
 

@@ -91,6 +91,7 @@ struct NlArgs {
     int *peer_flags[LJMD_MAX_RANKS];  // flag block ([2][LJMD_MAX_RANKS] ints) of every rank
     int *flags;                       // this rank's flag block (the peers write into it)
     int *dbg_exec;                    // debug: CTAs that executed the body of sharded step seq (or nullptr)
+    unsigned long long *dbg_time;     // LJMD_SLAB_TIMELINE: [1024][4] globaltimer of {first CTA start, last flag seen, last CTA end, publish}
     unsigned long long spin_budget_ns; // longest wait for the peers' flags before the run is declared dead
     int eval_sel;  // rebuild kernels: 0 = the list is for rb[cur], 1 = for rb[1-cur]
     unsigned long long *pair_counts;
@@ -675,6 +676,7 @@ nl_step_kernel(NlArgs a)
         if (threadIdx.x < 32) { // warp 0 decides; lanes 0 .. world-1 wait for one rank's flag each, in parallel
             const int lane = threadIdx.x;
             int viol = 0;
+            if (a.dbg_time && lane == 0 && seq < 1024) atomicMin(&a.dbg_time[4 * seq + 0], nl_globaltimer());
             if (lane == 0) {
                 const int layer = a.nc * a.nc;
                 const int owned = a.cell_start[a.xhi * layer] - a.cell_start[a.xlo * layer];
@@ -707,6 +709,7 @@ nl_step_kernel(NlArgs a)
                 }
             }
             if (lane == 0) s_viol = viol;
+            if (a.dbg_time && lane == 0 && viol == 0 && seq < 1024) atomicMax(&a.dbg_time[4 * seq + 1], nl_globaltimer());
         }
         __syncthreads();
         if (s_viol & 2) return;
@@ -825,6 +828,7 @@ nl_step_kernel(NlArgs a)
 #pragma unroll
         for (int q = 0; q < NL_NS; ++q) sp[q] = s[q];
         __threadfence();
+        if (SH && a.dbg_time && seq < 1024) atomicMax(&a.dbg_time[4 * seq + 2], nl_globaltimer());
         const unsigned t = atomicAdd(&a.ctl->ticket_step, 1u);
         is_last = (t == (unsigned)nact - 1);
     }
@@ -875,6 +879,7 @@ nl_step_kernel(NlArgs a)
             }
         }
         a.ctl->ticket_step = 0;
+        if (SH && a.dbg_time && seq < 1024) a.dbg_time[4 * seq + 3] = nl_globaltimer();
     }
 #if LJMD_NL_PUBLISH_IN_KERNEL
     if (SH && MODE == 1) {
@@ -1122,6 +1127,7 @@ static NlArgs make_args(ljmd_ctx *c, int eval_sel)
     for (int q = 0; q < LJMD_MAX_RANKS; ++q) { a.peer_p4[q] = w.peer_p4[q]; a.peer_flags[q] = w.peer_flags[q]; }
     a.flags = w.flags;
     a.dbg_exec = w.dbg_exec;
+    a.dbg_time = w.dbg_time;
     {
         const char *e = w.sh_on ? getenv("LJMD_SLAB_SPIN_TIMEOUT_S") : nullptr;
         const double budget_s = e ? atof(e) : 10.0;
@@ -1196,6 +1202,10 @@ int nlist_plan(ljmd_ctx *c)
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.mom, 0, sizeof(double) * 4, c->stream));
     LJMD_CUDA_CHECK(cudaMalloc(&w.ctl, sizeof(NlCtl)));
     LJMD_CUDA_CHECK(cudaMalloc(&w.flags, sizeof(int) * 2 * LJMD_MAX_RANKS));
+    if (getenv("LJMD_SLAB_TIMELINE")) {
+        LJMD_CUDA_CHECK(cudaMalloc(&w.dbg_time, sizeof(unsigned long long) * 4096));
+        LJMD_CUDA_CHECK(cudaMemsetAsync(w.dbg_time, 0, sizeof(unsigned long long) * 4096, c->stream));
+    }
     if (getenv("LJMD_SLAB_DEBUG")) {
         LJMD_CUDA_CHECK(cudaMalloc(&w.dbg_exec, sizeof(int) * 4096));
         LJMD_CUDA_CHECK(cudaMemsetAsync(w.dbg_exec, 0, sizeof(int) * 4096, c->stream));
@@ -1570,6 +1580,8 @@ extern "C" int ljmd_ctx_slab_attach(ljmd_ctx *c, int32_t rank, int32_t world, co
         w.own_blocks = (int)((1.3 * mean + 4096.0) / apb) + 1;
         if (w.own_blocks > w.nblk * w.tpa) w.own_blocks = w.nblk * w.tpa;
         if (c->graph_chunk) { cudaGraphExecDestroy(c->graph_chunk); c->graph_chunk = nullptr; }
+        for (int k = 0; k < 33; ++k)
+            if (c->graph_slab[k]) { cudaGraphExecDestroy(c->graph_slab[k]); c->graph_slab[k] = nullptr; }
         int zero4[5] = {0, 0, 0, 0, 0}; // halted, steps_left, steps_done, seq, pending_flag
         cudaError_t e = cudaMemcpyAsync(reinterpret_cast<char *>(w.ctl) + offsetof(NlCtl, halted), zero4, sizeof(zero4),
                                         cudaMemcpyHostToDevice, c->stream);
@@ -1745,6 +1757,20 @@ extern "C" int ljmd_ctx_slab_poison(ljmd_ctx *c)
     return LJMD_OK;
 }
 
+// Debug aid (LJMD_SLAB_TIMELINE=1 at context creation): per sharded step since the last call, the device
+// globaltimer (ns) of {first CTA start, last CTA past the flag wait, last CTA end, flag published}; re-arms.
+extern "C" int ljmd_ctx_debug_slab_timeline(ljmd_ctx *c, uint64_t *out, int32_t max_steps)
+{
+    if (!c || !out || !c->nw.dbg_time) return 0;
+    const int m = max_steps < 1024 ? max_steps : 1024;
+    cudaStreamSynchronize(c->stream);
+    if (cudaMemcpy(out, c->nw.dbg_time, sizeof(unsigned long long) * 4 * (size_t)m, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    std::vector<unsigned long long> init(4096, 0ull);
+    for (int k = 0; k < 1024; ++k) init[4 * k] = ~0ull; // slot 0 is a minimum
+    cudaMemcpy(c->nw.dbg_time, init.data(), sizeof(unsigned long long) * 4096, cudaMemcpyHostToDevice);
+    return m;
+}
+
 // Debug aid: XOR checksums of {next positions, v, a, packed next positions} over ALL slots.
 extern "C" int ljmd_ctx_debug_checksum(ljmd_ctx *c, uint64_t *out4)
 {
@@ -1809,15 +1835,51 @@ extern "C" int ljmd_ctx_slab_run(ljmd_ctx *c, int32_t max_steps, int32_t *steps_
     // (The rare wrong-velocity defect once blamed on adjacent step kernels had another cause -- every
     // thread tested ctl->halted itself -- fixed in the sharded prologue of nl_step_kernel, DESIGN.md 6.
     // LJMD_NL_PUBLISH_IN_KERNEL=1 builds publish from the step kernel's last CTA instead.)
-    for (int s = 0; s < max_steps && e == cudaSuccess && rc == LJMD_OK; ++s) {
-        rc = nlist_enqueue_step_kernel(c);
+    // The launches of a chunk are replayed as ONE CUDA graph (cached per chunk length): no per-launch host work,
+    // shorter gaps between dependent kernels.  LJMD_SLAB_GRAPH=0 issues them one by one.
+    const char *ge = getenv("LJMD_SLAB_GRAPH");
+    const bool use_graph = max_steps >= 2 && max_steps <= 32 && !(ge && atoi(ge) == 0);
+    auto enqueue_chunk = [&]() {
+        for (int s = 0; s < max_steps && rc == LJMD_OK; ++s) {
+            rc = nlist_enqueue_step_kernel(c);
 #if !LJMD_NL_PUBLISH_IN_KERNEL
-        if (rc == LJMD_OK) {
-            const NlArgs a = make_args(c, 0);
-            nl_publish_kernel<<<1, 32, 0, c->stream>>>(a);
-            c->launches++;
-        }
+            if (rc == LJMD_OK) {
+                const NlArgs a = make_args(c, 0);
+                nl_publish_kernel<<<1, 32, 0, c->stream>>>(a);
+                if (!c->capturing) c->launches++;
+            }
 #endif
+        }
+    };
+    if (use_graph && e == cudaSuccess) {
+        if (!c->graph_slab[max_steps]) {
+            const int cur_save = w.cur_host;
+            cudaGraph_t g = nullptr;
+            e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                c->capturing = true;
+                enqueue_chunk();
+                c->capturing = false;
+                const cudaError_t e2 = cudaStreamEndCapture(c->stream, &g);
+                if (e2 != cudaSuccess) e = e2;
+            }
+            w.cur_host = cur_save; // capture executes nothing
+            if (e == cudaSuccess && rc == LJMD_OK) e = cudaGraphInstantiate(&c->graph_slab[max_steps], g, 0);
+            if (g) cudaGraphDestroy(g);
+        }
+        if (e == cudaSuccess && rc == LJMD_OK) {
+            // the timed region starts after the (one-off) capture
+            e = cudaEventRecord(c->ev_s0, c->stream);
+            if (e == cudaSuccess) e = cudaGraphLaunch(c->graph_slab[max_steps], c->stream);
+            if (max_steps & 1) w.cur_host ^= 1; // what max_steps enqueue calls would have done to the host mirror
+#if LJMD_NL_PUBLISH_IN_KERNEL
+            c->launches += max_steps;
+#else
+            c->launches += 2 * (int64_t)max_steps;
+#endif
+        }
+    } else if (e == cudaSuccess) {
+        enqueue_chunk();
     }
     if (e == cudaSuccess) e = cudaEventRecord(c->ev_s1, c->stream);
     NlCtl h;

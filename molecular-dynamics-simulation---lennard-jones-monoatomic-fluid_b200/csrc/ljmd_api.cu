@@ -83,6 +83,8 @@ static void drop_graphs(ljmd_ctx *c)
     if (c->graph_compat) { cudaGraphExecDestroy(c->graph_compat); c->graph_compat = nullptr; }
     for (int k = 0; k < 16; ++k)
         if (c->graph_tail[k]) { cudaGraphExecDestroy(c->graph_tail[k]); c->graph_tail[k] = nullptr; }
+    for (int k = 0; k < 33; ++k)
+        if (c->graph_slab[k]) { cudaGraphExecDestroy(c->graph_slab[k]); c->graph_slab[k] = nullptr; }
 }
 
 struct DeviceGuard {

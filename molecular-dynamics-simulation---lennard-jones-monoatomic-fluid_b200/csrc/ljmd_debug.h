@@ -15,6 +15,11 @@ int ljmd_ctx_slab_publish(ljmd_ctx *ctx);
  * packed next positions} over all slots; equal on every rank right after a gather + rebuild. */
 int ljmd_ctx_debug_checksum(ljmd_ctx *ctx, uint64_t *out4);
 
+/* Debug aid (LJMD_SLAB_TIMELINE=1 at context creation): device globaltimer (ns) of {first CTA start, last CTA
+ * past the flag wait, last CTA end, flag published} for the sharded steps seq = 0 .. max_steps-1 recorded since
+ * the previous call (which re-arms the buffer; call it once before the run of interest).  Returns steps copied. */
+int ljmd_ctx_debug_slab_timeline(ljmd_ctx *ctx, uint64_t *out, int32_t max_steps);
+
 /* Tuning aid: per-warp {start, end, smid, items} clock records of the last independent-warp
  * all-pairs launch (context created with LJMD_SYM_DEBUG=1); returns the number of warps. */
 int ljmd_ctx_debug_warp_times(ljmd_ctx *ctx, long long *out, int max_warps);

@@ -180,6 +180,7 @@ struct NlistWork {
     void *ipc_p4[LJMD_MAX_RANKS], *ipc_flags[LJMD_MAX_RANKS];
     int *flags;
     int *dbg_exec;       // debug counters (LJMD_SLAB_DEBUG)
+    unsigned long long *dbg_time; // per-step device timestamps (LJMD_SLAB_TIMELINE)
 };
 
 } // namespace ljmd
@@ -214,6 +215,7 @@ struct ljmd_ctx {
     cudaGraphExec_t graph_chunk; // G steps
     cudaGraphExec_t graph_compat; // opt-in: one ljmd_verlet_step host-array call (upload, step, download)
     cudaGraphExec_t graph_tail[16]; // graph_tail[k]: 2k steps (the even remainder of a run after the 32-step chunks)
+    cudaGraphExec_t graph_slab[33]; // graph_slab[k]: k sharded steps (ljmd_ctx_slab_run with max_steps = k <= 32)
     int graph_chunk_steps;
     // series buffer
     double *d_series;

@@ -214,7 +214,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
     // (fixed shape => bit-reproducible).  One CTA walking all of them alone was the tail of this kernel: 19 k
     // work items at N = 32k cost it 60 us.
     double sl[3] = {0.0, 0.0, 0.0};
-    {
+    const bool two_level = a.n_spart > 1024; // few partials (small systems): the last CTA reads them directly, as before
+    if (two_level) {
         const int S = (a.n_spart + (int)gridDim.x - 1) / (int)gridDim.x;
         const int b0 = blockIdx.x * S, b1 = min(a.n_spart, b0 + S);
         const double *sp = a.spart + (size_t)rep * a.n_spart * 3;
@@ -223,8 +224,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
             sl[1] += sp[3 * b + 1];
             sl[2] += sp[3 * b + 2];
         }
+        block_sum<3>(sl, scratch);
     }
-    block_sum<3>(sl, scratch);
     if (threadIdx.x == 0) {
         double *kp = a.kpart + ((size_t)rep * gridDim.x + blockIdx.x) * 6;
         kp[0] = k[0]; kp[1] = k[1]; kp[2] = k[2];
@@ -245,9 +246,19 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
         kk[0] += __ldcg(kp + 6 * b + 0);
         kk[1] += __ldcg(kp + 6 * b + 1);
         kk[2] += __ldcg(kp + 6 * b + 2);
-        s[0] += __ldcg(kp + 6 * b + 3);
-        s[1] += __ldcg(kp + 6 * b + 4);
-        s[2] += __ldcg(kp + 6 * b + 5);
+        if (two_level) {
+            s[0] += __ldcg(kp + 6 * b + 3);
+            s[1] += __ldcg(kp + 6 * b + 4);
+            s[2] += __ldcg(kp + 6 * b + 5);
+        }
+    }
+    if (!two_level) {
+        const double *sp = a.spart + (size_t)rep * a.n_spart * 3;
+        for (int b = threadIdx.x; b < a.n_spart; b += blockDim.x) {
+            s[0] += __ldcg(sp + 3 * b + 0);
+            s[1] += __ldcg(sp + 3 * b + 1);
+            s[2] += __ldcg(sp + 3 * b + 2);
+        }
     }
     block_sum<3>(s, scratch);
     block_sum<3>(kk, scratch);

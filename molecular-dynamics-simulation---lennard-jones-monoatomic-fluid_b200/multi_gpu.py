@@ -127,6 +127,10 @@ class SlabRunner:
         ctx.slab_drift()     # r(t+dt) of every atom
         ctx.slab_rebuild()   # only if the drift already violated the skin of the t=0 list
         self.bounds = ctx.slab_bounds()
+        # one gather now (idempotent: every rank already holds the complete state): NCCL sets up its channels on
+        # the first collective of a size class, which would otherwise cost the first real rebuild a millisecond
+        self.gather()
+        self.stream.synchronize()
         dist.barrier(group=group)  # every rank is attached before anybody writes into a peer
 
     def _buffers(self, cmax: int):

@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import make_config, melt, rel_err
+from conftest import assert_forces_close, force_scale, make_config, melt, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
@@ -116,6 +116,7 @@ def test_nlist_vs_oracle_32k(lj, O):
         _, cut = ctx.pair_counts()
     assert cut == ncut
     assert rel_err(got.ax, ax) <= TOL and rel_err(got.ay, ay) <= TOL and rel_err(got.az, az) <= TOL
+    assert_forces_close((got.ax, got.ay, got.az), (ax, ay, az), force_scale(p_o.box_length, p_o.rc, *s[:3]), TOL)
     for g_, w_ in zip(obs, (e, d_, dd)):
         assert abs(g_ - w_) <= TOL * abs(w_)
 
@@ -134,6 +135,7 @@ def test_nlist_single_step_parity_32k(lj, O):
     for name, want in zip(lj.SimState.NAMES, ref):
         assert rel_err(getattr(s, name), want) <= TOL, name
     assert np.array_equal(s.rx, ref[0]) and np.array_equal(s.ry, ref[1]) and np.array_equal(s.rz, ref[2])
+    assert_forces_close((s.ax, s.ay, s.az), ref[6:9], force_scale(p_o.box_length, p_o.rc, *ref[:3]), TOL)
     lj.compat_release()
 
 

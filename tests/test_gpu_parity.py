@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import make_config, melt, rel_err
+from conftest import assert_forces_close, force_scale, make_config, melt, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
@@ -23,6 +23,8 @@ def _check_forces(lj, O, p_o, arrs, tol=TOL):
     e, d, dd = lj.compute_lj_potential_energy(p, s)
     ax, ay, az, e0, d0, dd0 = O.compute_lj(p_o, *arrs[:3])
     assert rel_err(s.ax, ax) <= tol and rel_err(s.ay, ay) <= tol and rel_err(s.az, az) <= tol
+    # ... and per atom, relative to the sum of the magnitudes of the pair forces on that atom
+    assert_forces_close((s.ax, s.ay, s.az), (ax, ay, az), force_scale(p_o.box_length, p_o.rc, *arrs[:3]), tol)
     assert abs(e - e0) <= tol * abs(e0)
     assert abs(d - d0) <= tol * abs(d0)
     assert abs(dd - dd0) <= tol * abs(dd0)
@@ -79,6 +81,8 @@ def test_verlet_step_cfg2(lj, O):
         assert rel_err(getattr(s, name), want) <= TOL, name
     # positions and half-kicked velocities use the reference's exact operation order
     assert np.array_equal(s.rx, ref[0]) and np.array_equal(s.ry, ref[1]) and np.array_equal(s.rz, ref[2])
+    # accelerations per atom, relative to the sum of the magnitudes of the pair forces on that atom
+    assert_forces_close((s.ax, s.ay, s.az), ref[6:9], force_scale(p_o.box_length, p_o.rc, *ref[:3]), TOL)
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 127, 128, 129, 500, 1000, 1537])
@@ -211,6 +215,39 @@ def test_replicas_are_independent(lj, O):
         ro = O.run_steps(p_o, 20, ref)
         assert np.all(np.abs(obs[r] - ro) <= 1e-10 * np.abs(ro))
         assert rel_err(d.rx[r], ref[0]) < 1e-10
+
+
+def test_cfg5_64_replicas_per_context(lj, O):
+    """BASELINE.json configs[4] as specified: 64 replicas of the shipped N = 500 system in ONE context, replica r
+    started with the velocity seed -(12345 + r).  Every replica, single step from identical states: the four
+    observables to 1e-12, positions bitwise, velocities and accelerations to 1e-12 (per atom for the latter)."""
+    p_o, _ = make_config(O, "cfg1")
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    R = 64
+    states = []
+    for r in range(R):
+        s_r, _, _ = O.initial_config(p_o, -(12345 + r), -555.0)
+        states.append(melt(O, p_o, s_r, 40))        # off the perfect lattice
+    batched = [np.ascontiguousarray(np.stack([states[r][k] for r in range(R)])) for k in range(9)]
+    with lj.Context(p, method=lj.METHOD_ALLPAIRS, nreplicas=R) as ctx:
+        ctx.upload(lj.SimState.from_arrays(batched))
+        obs = ctx.step(1)
+        d = ctx.download()
+    assert obs.shape == (R, 4)
+    for r in range(R):
+        ref = [a.copy() for a in states[r]]
+        ro = O.verlet_step(p_o, ref)
+        assert np.all(np.abs(obs[r] - ro) <= TOL * np.abs(ro)), r
+        got = [a[r] for a in d.arrays()]
+        for k in range(3):
+            assert np.array_equal(got[k], ref[k])
+            assert rel_err(got[3 + k], ref[3 + k]) <= TOL
+        if r % 16 == 0:
+            scale = force_scale(p_o.box_length, p_o.rc, *ref[:3])
+            assert_forces_close(got[6:9], ref[6:9], scale, TOL)
+        else:
+            for k in range(3):
+                assert rel_err(got[6 + k], ref[6 + k]) <= TOL
 
 
 def test_kinetic_energy_driver_order(lj, O):

@@ -14,7 +14,5 @@ run base 8 LJMD_X=0
 run pub 8 LJMD_LIB_PATH=$P/lib/libljmd_pub.so
 run pipe1 8 LJMD_NL_PIPE=1
 run pub_skin04 8 LJMD_LIB_PATH=$P/lib/libljmd_pub.so LJMD_NL_SKIN=0.4
-run pub_tpa4 8 LJMD_LIB_PATH=$P/lib/libljmd_pub.so LJMD_NL_TPA=4
 run pub 4 LJMD_LIB_PATH=$P/lib/libljmd_pub.so
-run pub 2 LJMD_LIB_PATH=$P/lib/libljmd_pub.so
 ls -la $O
