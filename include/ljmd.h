@@ -228,6 +228,18 @@ int ljmd_ctx_slab_rebuild(ljmd_ctx *ctx, int32_t force);
 int ljmd_ctx_slab_run(ljmd_ctx *ctx, int32_t max_steps, int32_t *steps_done, int32_t *halted,
                       double *obs4);
 
+/* Slab-LOCAL rebuild (needs >= 2 ranks and >= 2 cell layers per rank): instead of the all-gather + global re-sort,
+ * every rank exchanges two cell layers with each neighbour and re-sorts its own slab and halo layers only; the cell
+ * table stays global through ONE all-reduce of the cell histogram.  Same slots, lists and results as the global
+ * path, bit for bit.  Sequence (multi_gpu.SlabRunner.rebuild_local):
+ *   halo(buf, cap, side, 0) x 2 -> [host: send / recv with the neighbours] -> halo(buf, cap, side, 1) x 2
+ *   -> rebuild_local(0) -> [host: all-reduce(sum, int32) of the ncells ints at *cell_count_ptr] -> rebuild_local(1).
+ * side 0 = towards / from the left neighbour, 1 = right.  Buffers: (halo_narr x cap) doubles, cap >= *halo_cap. */
+int ljmd_ctx_slab_local_info(ljmd_ctx *ctx, uint64_t *cell_count_ptr, int32_t *ncells, int32_t *halo_cap,
+                             int32_t *halo_narr);
+int ljmd_ctx_slab_halo(ljmd_ctx *ctx, double *dev_buf, int32_t cap, int32_t side, int32_t unpack);
+int ljmd_ctx_slab_rebuild_local(ljmd_ctx *ctx, int32_t phase);
+
 /* Self-check of the neighbour-list path: total momentum (sum of v) of the atoms handled by the last
  * step launch -- an invariant of the dynamics (a sharded run adds the ranks' shares). */
 int ljmd_ctx_nlist_momentum(ljmd_ctx *ctx, double *p3);

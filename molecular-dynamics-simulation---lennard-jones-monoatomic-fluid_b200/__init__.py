@@ -91,7 +91,8 @@ ABI_SYMBOLS = [
     "ljmd_ctx_nlist_info", "ljmd_ctx_download_nlist",
     "ljmd_ctx_slab_export", "ljmd_ctx_slab_attach", "ljmd_ctx_slab_bounds", "ljmd_ctx_slab_pack",
     "ljmd_ctx_slab_unpack", "ljmd_ctx_slab_drift", "ljmd_ctx_slab_rebuild", "ljmd_ctx_slab_run",
-    "ljmd_ctx_slab_poison", "ljmd_ctx_series_arm", "ljmd_ctx_series_fetch",
+    "ljmd_ctx_slab_poison", "ljmd_ctx_slab_local_info", "ljmd_ctx_slab_halo", "ljmd_ctx_slab_rebuild_local",
+    "ljmd_ctx_series_arm", "ljmd_ctx_series_fetch",
     "ljmd_ctx_nlist_momentum", "ljmd_rdf_histogram", "ljmd_time_correlation",
 ]
 # Tuning / debug exports declared in csrc/ljmd_debug.h, not in the product header.
@@ -489,6 +490,18 @@ class Context:
 
     def slab_rebuild(self, force: bool = False) -> None:
         _chk(self._L.ljmd_ctx_slab_rebuild(self._h, 1 if force else 0))
+
+    def slab_local_info(self):
+        """(device address of the int32 cell histogram, ncells, halo_cap, halo_narr) of a slab-local rebuild."""
+        ptr, nc, cap, na = C.c_uint64(), C.c_int32(), C.c_int32(), C.c_int32()
+        _chk(self._L.ljmd_ctx_slab_local_info(self._h, C.byref(ptr), C.byref(nc), C.byref(cap), C.byref(na)))
+        return int(ptr.value), nc.value, cap.value, na.value
+
+    def slab_halo(self, dev_ptr: int, cap: int, side: int, unpack: bool) -> None:
+        _chk(self._L.ljmd_ctx_slab_halo(self._h, C.c_void_p(dev_ptr), int(cap), int(side), 1 if unpack else 0))
+
+    def slab_rebuild_local(self, phase: int) -> None:
+        _chk(self._L.ljmd_ctx_slab_rebuild_local(self._h, int(phase)))
 
     def debug_checksum(self):
         out = (C.c_uint64 * 4)()

@@ -93,6 +93,12 @@ struct NlArgs {
     int *dbg_exec;                    // debug: CTAs that executed the body of sharded step seq (or nullptr)
     unsigned long long *dbg_time;     // LJMD_SLAB_TIMELINE: [1024][4] globaltimer of {first CTA start, last flag seen, last CTA end, publish}
     unsigned long long spin_budget_ns; // longest wait for the peers' flags before the run is declared dead
+    // slab-LOCAL rebuild (sl_on): the sort kernels work on slot pieces instead of [0, n).  sl_rng (device):
+    // [0..2] start, [3..5] length of the CANDIDATE pieces {left neighbour's last two cell layers, the own slab,
+    // right neighbour's first two layers} under the OLD cell table, [6] their total; [8..10], [11..13], [14]: the
+    // same for the TARGET pieces {left halo layer, own slab, right halo layer} under the NEW cell table.
+    int sl_on;
+    const int *sl_rng;
     int eval_sel;  // rebuild kernels: 0 = the list is for rb[cur], 1 = for rb[1-cur]
     unsigned long long *pair_counts;
 };
@@ -137,6 +143,26 @@ __device__ __forceinline__ int nl_cell_coord(double x, double L, double invL, do
     return min(c, nc - 1);
 }
 
+// Slab-local rebuild: t-th slot of the three pieces at rng[0..2] / rng[3..5]; -1 past the end.
+__device__ __forceinline__ int nl_sl_slot(const int *rng, int t)
+{
+    if (t < rng[3]) return rng[0] + t;
+    t -= rng[3];
+    if (t < rng[4]) return rng[1] + t;
+    t -= rng[4];
+    return t < rng[5] ? rng[2] + t : -1;
+}
+// Cell layer (x index) of cell c relative to the owned layers: -1 = left halo layer, 0 .. = owned, nown = right
+// halo layer, anything else = not this rank's business.  Periodic.
+__device__ __forceinline__ int nl_sl_rel_layer(const NlArgs &a, int c)
+{
+    const int cx = c / (a.nc * a.nc);
+    if (cx >= a.xlo && cx < a.xhi) return cx - a.xlo;
+    if (cx == (a.xlo - 1 + a.nc) % a.nc) return -1;
+    if (cx == a.xhi % a.nc) return a.xhi - a.xlo;
+    return -2;
+}
+
 // ------------------------------------------------------------------------------------------
 // Rebuild sequence.  Every kernel returns at once unless ctl->need_rebuild is set.
 // ------------------------------------------------------------------------------------------
@@ -144,8 +170,9 @@ __global__ void __launch_bounds__(256) nl_bin_kernel(NlArgs a)
 {
     if (!a.ctl->need_rebuild) return;
     const int n = a.sc.n;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.sl_on) k = nl_sl_slot(a.sl_rng, k); // candidates of a slab-local rebuild
+    if (k >= n || k < 0) return;
     const double *px = a.rb[a.ctl->cur ^ a.eval_sel];
     bool outside = false;
     const int cx = nl_cell_coord(px[k], a.sc.L, a.sc.invL, a.scale, a.nc, outside);
@@ -153,7 +180,9 @@ __global__ void __launch_bounds__(256) nl_bin_kernel(NlArgs a)
     const int cz = nl_cell_coord(px[2 * (size_t)n + k], a.sc.L, a.sc.invL, a.scale, a.nc, outside);
     const int c = (cx * a.nc + cy) * a.nc + cz;
     a.cell_of_slot[k] = c;
-    atomicAdd(&a.cell_count[c], 1); // integer histogram: order-independent
+    // integer histogram: order-independent.  Slab-local: every rank counts the cells of its OWN layers only (it
+    // sees every atom that can end up there); the ranks' histograms are then added by one all-reduce.
+    if (!a.sl_on || (cx >= a.xlo && cx < a.xhi)) atomicAdd(&a.cell_count[c], 1);
     if (outside) a.ctl->unwrapped = 1;
 }
 
@@ -224,9 +253,11 @@ __global__ void __launch_bounds__(1024) nl_scan_add_kernel(NlArgs a)
 __global__ void __launch_bounds__(256) nl_fill_kernel(NlArgs a)
 {
     if (!a.ctl->need_rebuild) return;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= a.sc.n) return;
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.sl_on) k = nl_sl_slot(a.sl_rng, k); // candidates (pieces saved before the scan replaced the cell table)
+    if (k >= a.sc.n || k < 0) return;
     const int c = a.cell_of_slot[k];
+    if (a.sl_on && nl_sl_rel_layer(a, c) == -2) return; // ends up in a cell this rank neither owns nor sees
     const int pos = a.cell_start[c] + atomicAdd(&a.cell_cursor[c], 1);
     a.keys[pos] = ((unsigned long long)(unsigned)a.orig[k] << 32) | (unsigned)k;
 }
@@ -235,7 +266,14 @@ __global__ void __launch_bounds__(256) nl_fill_kernel(NlArgs a)
 __global__ void __launch_bounds__(128) nl_sortcell_kernel(NlArgs a)
 {
     if (!a.ctl->need_rebuild) return;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.sl_on) { // the cells of the left halo layer, the owned layers and the right halo layer
+        const int layer = a.nc * a.nc, nl = a.xhi - a.xlo + 2;
+        if (c >= nl * layer) return;
+        const int li = c / layer - 1; // -1 .. nown
+        const int cx = li < 0 ? (a.xlo - 1 + a.nc) % a.nc : (a.xlo + li) % a.nc;
+        c = cx * layer + c % layer;
+    }
     if (c >= a.ncells) return;
     const int b = a.cell_start[c], e = a.cell_start[c + 1];
     for (int k = b + 1; k < e; ++k) {
@@ -251,8 +289,9 @@ __global__ void __launch_bounds__(256) nl_permute_kernel(NlArgs a)
 {
     if (!a.ctl->need_rebuild) return;
     const int n = a.sc.n;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.sl_on) k = nl_sl_slot(a.sl_rng + 8, k); // target slots: halo layer | own slab | halo layer, new cell table
+    if (k >= n || k < 0) return;
     const unsigned long long key = a.keys[k];
     const int old = (int)(key & 0xffffffffu), o = (int)(key >> 32);
     for (int q = 0; q < a.narr; ++q) a.alt[(size_t)q * n + k] = a.arr[q][old];
@@ -264,14 +303,47 @@ __global__ void __launch_bounds__(256) nl_copyback_kernel(NlArgs a)
 {
     if (!a.ctl->need_rebuild) return;
     const int n = a.sc.n;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.sl_on) k = nl_sl_slot(a.sl_rng + 8, k);
+    if (k >= n || k < 0) return;
     for (int q = 0; q < a.narr; ++q) a.arr[q][k] = a.alt[(size_t)q * n + k];
     a.orig[k] = a.orig_alt[k];
     // packed copy of the positions the list is built for (arrays 0-2 are rb[0], 3-5 rb[1])
     const int ev = a.ctl->cur ^ a.eval_sel;
     nl_st_pos(a.p4[ev] + k, a.alt[(size_t)(3 * ev) * n + k], a.alt[(size_t)(3 * ev + 1) * n + k],
               a.alt[(size_t)(3 * ev + 2) * n + k]);
+}
+
+// Slab-local rebuild: slot pieces from the cell table.  which = 0 (before the scan, OLD table): candidates =
+// {two layers left of the slab, the slab, two layers right of it}; which = 1 (after the scan, NEW table):
+// targets = {one layer, the slab, one layer}.  With >= 2 layers per rank every piece is contiguous.
+__global__ void nl_sl_ranges_kernel(NlArgs a, int *rng, int which)
+{
+    if (threadIdx.x != 0 || !a.ctl->need_rebuild) return;
+    const int layer = a.nc * a.nc, h = which ? 1 : 2;
+    const int l0 = ((a.xlo - h) % a.nc + a.nc) % a.nc, l2 = a.xhi % a.nc;
+    int *r = rng + 8 * which;
+    r[0] = a.cell_start[l0 * layer]; r[3] = a.cell_start[(l0 + h) * layer] - r[0];
+    r[1] = a.cell_start[a.xlo * layer]; r[4] = a.cell_start[a.xhi * layer] - r[1];
+    r[2] = a.cell_start[l2 * layer]; r[5] = a.cell_start[(l2 + h) * layer] - r[2];
+    r[6] = r[3] + r[4] + r[5];
+}
+
+// Two cell layers (first cell layer l0, periodic) of every permuted state array + the original indices <->
+// a dense buffer [narr + 1][cap]: what a rank sends to / receives from a neighbour at a slab-local rebuild.
+__global__ void __launch_bounds__(256) nl_halo_pack_kernel(NlArgs a, double *buf, int cap, int l0, int unpack)
+{
+    const int layer = a.nc * a.nc;
+    const int sb = a.cell_start[l0 * layer], cnt = min(cap, a.cell_start[(l0 + 2) * layer] - sb);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    if (!unpack) {
+        for (int q = 0; q < a.narr; ++q) buf[(size_t)q * cap + t] = a.arr[q][sb + t];
+        buf[(size_t)a.narr * cap + t] = (double)a.orig[sb + t];
+    } else {
+        for (int q = 0; q < a.narr; ++q) a.arr[q][sb + t] = buf[(size_t)q * cap + t];
+        a.orig[sb + t] = (int)buf[(size_t)a.narr * cap + t];
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -837,8 +909,23 @@ nl_step_kernel(NlArgs a)
     __threadfence();
 
     // fixed-order reduction of all CTA partials
+    // (the loads of four rows are issued before the first add: this loop is a chain of L2 round trips -- at
+    // 8192 CTAs it was 25 us of a 294 us kernel -- the adds keep their order, so the sums are unchanged bit for bit)
     double r[NL_NS] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int b = threadIdx.x; b < (SH ? nact : (int)gridDim.x); b += NL_BS) {
+    const int nrow = SH ? nact : (int)gridDim.x;
+    int b = threadIdx.x;
+    for (; b + 3 * NL_BS < nrow; b += 4 * NL_BS) {
+        double v[4][NL_NS];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int q = 0; q < NL_NS; ++q) v[u][q] = __ldcg(a.spart + (size_t)(b + u * NL_BS) * NL_NS + q);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int q = 0; q < NL_NS; ++q) r[q] += v[u][q];
+    }
+    for (; b < nrow; b += NL_BS) {
 #pragma unroll
         for (int q = 0; q < NL_NS; ++q) r[q] += __ldcg(a.spart + (size_t)b * NL_NS + q);
     }
@@ -1054,9 +1141,10 @@ __global__ void __launch_bounds__(256) nl_pack_kernel(NlArgs a, double *buf, int
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= cnt) return;
     for (int q = 0; q < a.narr; ++q) buf[(size_t)q * cmax + t] = a.arr[q][sb + t];
+    buf[(size_t)a.narr * cmax + t] = (double)a.orig[sb + t]; // after slab-local rebuilds only the owner knows them
 }
 
-// recv = [world][narr][cmax]; bounds[q] = first cell layer of rank q (bounds[world] = nc)
+// recv = [world][narr + 1][cmax]; bounds[q] = first cell layer of rank q (bounds[world] = nc)
 struct NlBounds { int x[LJMD_MAX_RANKS + 1]; };
 __global__ void __launch_bounds__(256) nl_unpack_kernel(NlArgs a, const double *recv, int cmax, NlBounds bd)
 {
@@ -1066,8 +1154,9 @@ __global__ void __launch_bounds__(256) nl_unpack_kernel(NlArgs a, const double *
     const int sb = a.cell_start[bd.x[q] * layer], cnt = a.cell_start[bd.x[q + 1] * layer] - sb;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= cnt) return;
-    const double *src = recv + (size_t)q * a.narr * cmax;
+    const double *src = recv + (size_t)q * (a.narr + 1) * cmax;
     for (int k = 0; k < a.narr; ++k) a.arr[k][sb + t] = src[(size_t)k * cmax + t];
+    a.orig[sb + t] = (int)src[(size_t)a.narr * cmax + t];
 }
 
 // ==========================================================================================
@@ -1124,6 +1213,7 @@ static NlArgs make_args(ljmd_ctx *c, int eval_sel)
     a.eval_sel = eval_sel;
     a.pair_counts = nullptr;
     a.sh_on = w.sh_on; a.rank = w.rank; a.world = w.world; a.xlo = w.xlo; a.xhi = w.xhi;
+    a.sl_on = 0; a.sl_rng = w.sl_rng;
     for (int q = 0; q < LJMD_MAX_RANKS; ++q) { a.peer_p4[q] = w.peer_p4[q]; a.peer_flags[q] = w.peer_flags[q]; }
     a.flags = w.flags;
     a.dbg_exec = w.dbg_exec;
@@ -1202,6 +1292,8 @@ int nlist_plan(ljmd_ctx *c)
     LJMD_CUDA_CHECK(cudaMemsetAsync(w.mom, 0, sizeof(double) * 4, c->stream));
     LJMD_CUDA_CHECK(cudaMalloc(&w.ctl, sizeof(NlCtl)));
     LJMD_CUDA_CHECK(cudaMalloc(&w.flags, sizeof(int) * 2 * LJMD_MAX_RANKS));
+    LJMD_CUDA_CHECK(cudaMalloc(&w.sl_rng, sizeof(int) * 16));
+    LJMD_CUDA_CHECK(cudaMemsetAsync(w.sl_rng, 0, sizeof(int) * 16, c->stream));
     if (getenv("LJMD_SLAB_TIMELINE")) {
         LJMD_CUDA_CHECK(cudaMalloc(&w.dbg_time, sizeof(unsigned long long) * 4096));
         LJMD_CUDA_CHECK(cudaMemsetAsync(w.dbg_time, 0, sizeof(unsigned long long) * 4096, c->stream));
@@ -1236,6 +1328,7 @@ void nlist_free(ljmd_ctx *c)
         if (w.ipc_flags[q]) cudaIpcCloseMemHandle(w.ipc_flags[q]);
     }
     cudaFree(w.flags);
+    cudaFree(w.sl_rng);
     if (w.side_stream) cudaStreamDestroy(w.side_stream);
 }
 
@@ -1579,6 +1672,9 @@ extern "C" int ljmd_ctx_slab_attach(ljmd_ctx *c, int32_t rank, int32_t world, co
         const int apb = NL_BS / w.tpa;
         w.own_blocks = (int)((1.3 * mean + 4096.0) / apb) + 1;
         if (w.own_blocks > w.nblk * w.tpa) w.own_blocks = w.nblk * w.tpa;
+        // slab-local rebuild: two cell layers of a neighbour (30 % above the mean + slack), and all candidates
+        w.sl_halo_cap = (int)(2.0 * (1.3 * (double)c->sc.n / w.nc + 1024.0));
+        w.sl_cand_cap = std::min(c->sc.n, w.own_blocks * apb + 2 * w.sl_halo_cap);
         if (c->graph_chunk) { cudaGraphExecDestroy(c->graph_chunk); c->graph_chunk = nullptr; }
         for (int k = 0; k < 33; ++k)
             if (c->graph_slab[k]) { cudaGraphExecDestroy(c->graph_slab[k]); c->graph_slab[k] = nullptr; }
@@ -1613,7 +1709,7 @@ extern "C" int ljmd_ctx_slab_pack(ljmd_ctx *c, double *dev_buf, int32_t cmax, in
     clear_error();
     if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_slab_pack(): ctx is NULL.");
     if (!c->nw.sh_on) return set_error(LJMD_ERR_ARG, "ljmd_ctx_slab_pack(): context is not sharded.");
-    if (narr) *narr = c->nw.narr;
+    if (narr) *narr = c->nw.narr + 1; // the state arrays + the original atom indices
     if (!dev_buf) return LJMD_OK; // query only
     int prev = 0;
     LJMD_CUDA_CHECK(cudaGetDevice(&prev));
@@ -1694,6 +1790,102 @@ extern "C" int ljmd_ctx_slab_rebuild(ljmd_ctx *c, int32_t force)
                 fprintf(stderr, "[ljmd slab debug] rank %d: rebuild changed the per-atom checksum of %s\n", c->nw.rank, names[q]);
     }
     if (rc == LJMD_OK) rc = nlist_check_overflow(c);
+    if (prev != c->device) cudaSetDevice(prev);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Slab-LOCAL rebuild: no rank touches more than its own slab and two cell layers of each neighbour.
+//   1. ljmd_ctx_slab_halo(pack, side 0 / 1): my first / last two cell layers (all permuted state arrays + original
+//      indices) -> send buffers; the host exchanges them with the two neighbours (NCCL send / recv);
+//      ljmd_ctx_slab_halo(unpack, side 0 / 1): the left neighbour's last / the right neighbour's first two layers
+//      -> their global slots in this rank's arrays.  The cell table is still the old, globally identical one, so
+//      both sides agree on every count and slot.
+//   2. ljmd_ctx_slab_rebuild_local(0): cell of every CANDIDATE (own slab + the four received layers: every atom
+//      that can now be in an owned cell or in the two halo layers, because nobody moved more than skin/2 < one cell);
+//      histogram of the OWN layers' cells.  Host: ONE all-reduce (sum, int32) of the histogram over the ranks
+//      (ljmd_ctx_slab_local_info gives the device address) -> the complete, globally identical new histogram.
+//   3. ljmd_ctx_slab_rebuild_local(1): exclusive scan (-> new global cell table), scatter + per-cell sort by original
+//      index (the stable counting sort: same slots as the global sort, bit-exact) of the own and halo cells,
+//      permutation of their state, neighbour lists of the own slab.
+// Afterwards this rank's arrays are current for the own slab and the two halo layers only; ljmd_ctx_slab_pack /
+// _unpack (a full gather) make them complete again (SlabRunner.finish()).  Needs >= 2 cell layers per rank.
+// ------------------------------------------------------------------------------------------
+extern "C" int ljmd_ctx_slab_local_info(ljmd_ctx *c, uint64_t *cell_count_ptr, int32_t *ncells, int32_t *halo_cap,
+                                        int32_t *halo_narr)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_slab_local_info(): ctx is NULL.");
+    if (!c->nw.sh_on) return set_error(LJMD_ERR_ARG, "ljmd_ctx_slab_local_info(): context is not sharded.");
+    if (c->nw.world < 2 || c->nw.nc < 2 * c->nw.world)
+        return set_error(LJMD_ERR_UNSUPPORTED, "ljmd_ctx_slab_local_info(): a slab-local rebuild needs >= 2 ranks and >= 2 cell layers per rank.");
+    if (cell_count_ptr) *cell_count_ptr = (uint64_t)(uintptr_t)c->nw.cell_count;
+    if (ncells) *ncells = c->nw.ncells;
+    if (halo_cap) *halo_cap = c->nw.sl_halo_cap;
+    if (halo_narr) *halo_narr = c->nw.narr + 1;
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_ctx_slab_halo(ljmd_ctx *c, double *dev_buf, int32_t cap, int32_t side, int32_t unpack)
+{
+    clear_error();
+    if (!c || !dev_buf) return set_error(LJMD_ERR_NULL, "ljmd_ctx_slab_halo(): NULL argument.");
+    if (!c->nw.sh_on) return set_error(LJMD_ERR_ARG, "ljmd_ctx_slab_halo(): context is not sharded.");
+    if (cap < c->nw.sl_halo_cap) return set_error(LJMD_ERR_ARG, "ljmd_ctx_slab_halo(): cap %d < %d.", cap, c->nw.sl_halo_cap);
+    int prev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
+    const NlistWork &w = c->nw;
+    const NlArgs a = make_args(c, 1);
+    int l0;
+    if (!unpack) l0 = side == 0 ? w.xlo : w.xhi - 2;                                  // mine: first / last two layers
+    else l0 = side == 0 ? ((w.xlo - 2) % w.nc + w.nc) % w.nc : w.xhi % w.nc;          // the neighbours'
+    nl_halo_pack_kernel<<<(cap + 255) / 256, 256, 0, c->stream>>>(a, dev_buf, cap, l0, unpack ? 1 : 0);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (prev != c->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return set_error(LJMD_ERR_CUDA, "ljmd_ctx_slab_halo(): %s", cudaGetErrorString(e));
+    return LJMD_OK;
+}
+
+extern "C" int ljmd_ctx_slab_rebuild_local(ljmd_ctx *c, int32_t phase)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_slab_rebuild_local(): ctx is NULL.");
+    if (!c->nw.sh_on) return set_error(LJMD_ERR_ARG, "ljmd_ctx_slab_rebuild_local(): context is not sharded.");
+    int prev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
+    NlistWork &w = c->nw;
+    NlArgs a = make_args(c, 1);
+    a.sl_on = 1;
+    int rc = LJMD_OK;
+    cudaError_t e = cudaSuccess;
+    const int nb_cand = (w.sl_cand_cap + 255) / 256;
+    if (phase == 0) {
+        nl_clear_viol_kernel<<<1, 32, 0, c->stream>>>(w.flags, w.ctl);
+        const int zero = 0; // the halt is over; async copy from pageable memory returns after staging
+        e = cudaMemcpyAsync(reinterpret_cast<char *>(w.ctl) + offsetof(NlCtl, halted), &zero, sizeof(int), cudaMemcpyHostToDevice, c->stream);
+        nl_sl_ranges_kernel<<<1, 32, 0, c->stream>>>(a, w.sl_rng, 0);
+        nl_bin_kernel<<<nb_cand, 256, 0, c->stream>>>(a);
+        c->launches += 3;
+    } else {
+        const int ntiles = (w.ncells + 1023) / 1024;
+        const int ncell_tgt = (w.xhi - w.xlo + 2) * w.nc * w.nc;
+        nl_scan_tiles_kernel<<<ntiles, 1024, 0, c->stream>>>(a);
+        nl_scan_sums_kernel<<<1, 1024, 0, c->stream>>>(a, ntiles);
+        nl_scan_add_kernel<<<ntiles, 1024, 0, c->stream>>>(a);
+        nl_sl_ranges_kernel<<<1, 32, 0, c->stream>>>(a, w.sl_rng, 1);
+        nl_fill_kernel<<<nb_cand, 256, 0, c->stream>>>(a);
+        nl_sortcell_kernel<<<(ncell_tgt + 127) / 128, 128, 0, c->stream>>>(a);
+        nl_permute_kernel<<<nb_cand, 256, 0, c->stream>>>(a);
+        nl_copyback_kernel<<<nb_cand, 256, 0, c->stream>>>(a);
+        nl_build_kernel<<<w.nunits, NL_BS, w.smem_bytes, c->stream>>>(a);
+        c->launches += 9;
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) rc = set_error(LJMD_ERR_CUDA, "ljmd_ctx_slab_rebuild_local(): %s", cudaGetErrorString(e));
+    if (rc == LJMD_OK && phase != 0) rc = nlist_check_overflow(c);
     if (prev != c->device) cudaSetDevice(prev);
     return rc;
 }

@@ -179,6 +179,8 @@ struct NlistWork {
     int *peer_flags[LJMD_MAX_RANKS];
     void *ipc_p4[LJMD_MAX_RANKS], *ipc_flags[LJMD_MAX_RANKS];
     int *flags;
+    int *sl_rng;         // device [16]: slot pieces of a slab-local rebuild (see NlArgs::sl_rng)
+    int sl_cand_cap, sl_halo_cap; // launch sizes: candidate slots of a local rebuild, atoms of two cell layers
     int *dbg_exec;       // debug counters (LJMD_SLAB_DEBUG)
     unsigned long long *dbg_time; // per-step device timestamps (LJMD_SLAB_TIMELINE)
 };

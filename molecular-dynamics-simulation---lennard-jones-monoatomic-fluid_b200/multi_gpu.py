@@ -94,8 +94,13 @@ class SlabRunner:
     Per step nothing goes through the host or NCCL: the step kernels push their boundary layers
     into the neighbours' position buffers over NVLink and synchronise through per-step flags.
     torch.distributed is used (i) once, to exchange the CUDA IPC handles, and (ii) whenever a rank
-    reports a skin violation: one all-gather of the packed slabs, after which every rank re-sorts
-    globally and rebuilds the lists of its own slab.
+    reports a skin violation.  Then, by default (`rebuild_local`): two cell layers are exchanged with
+    each of the two neighbours (NCCL send / recv), the cell histogram is completed by ONE all-reduce,
+    and every rank re-sorts and rebuilds its own slab and halo layers only -- nothing scales with the
+    whole system.  LJMD_SLAB_LOCAL=0 (or fewer than two cell layers per rank) selects the first
+    version: one all-gather of the packed slabs, after which every rank re-sorts globally.  Both give
+    the same slots, lists and trajectory, bit for bit.  After local rebuilds a rank holds current data
+    for its slab and halo only; finish() gathers the complete state.
 
     `ctx` must hold the COMPLETE state (uploaded on every rank) with forces computed
     (ctx.compute_forces()).  Reference semantics of a step: physics/verlet.f90:41-97.
@@ -123,6 +128,17 @@ class SlabRunner:
         self.steps = 0
         import os
         self.debug = bool(os.environ.get("LJMD_SLAB_DEBUG_PY"))
+        self.local = False
+        if world >= 2 and os.environ.get("LJMD_SLAB_LOCAL", "1") != "0":
+            try:
+                ptr, ncells, cap, na = ctx.slab_local_info()
+                self.local = True
+            except Exception:
+                self.local = False  # fewer than two cell layers per rank: global re-sort
+        if self.local:
+            self.hist = torch.as_tensor(DeviceArray(ptr, ncells, "<i4"), device=self.dev)
+            self.halo_cap = cap
+            self.halo = [torch.empty(na * cap, dtype=torch.float64, device=self.dev) for _ in range(4)]  # sendL sendR recvL recvR
         self.t_run_dev_ms = self.t_run = self.t_gather = self.t_rebuild = 0.0  # profile of step()
         ctx.slab_drift()     # r(t+dt) of every atom
         ctx.slab_rebuild()   # only if the drift already violated the skin of the t=0 list
@@ -130,6 +146,10 @@ class SlabRunner:
         # one gather now (idempotent: every rank already holds the complete state): NCCL sets up its channels on
         # the first collective of a size class, which would otherwise cost the first real rebuild a millisecond
         self.gather()
+        if self.local:  # the same for the point-to-point channels and the histogram all-reduce of a local rebuild
+            with torch.cuda.stream(self.stream):
+                self._exchange_halos()
+                dist.all_reduce(torch.zeros_like(self.hist), group=group)
         self.stream.synchronize()
         dist.barrier(group=group)  # every rank is attached before anybody writes into a peer
 
@@ -149,6 +169,32 @@ class SlabRunner:
             self.ctx.slab_pack(send.data_ptr(), cmax)
             self.dist.all_gather_into_tensor(recv, send, group=self.group)
             self.ctx.slab_unpack(recv.data_ptr(), cmax)
+
+    def _exchange_halos(self) -> None:
+        """send buffers -> the two neighbours, their buffers -> recv (NCCL send / recv on the current stream)."""
+        dist = self.dist
+        send_l, send_r, recv_l, recv_r = self.halo
+        left, right = (self.rank - 1) % self.world, (self.rank + 1) % self.world
+        # send right first, receive from the left first: with two ranks both neighbours are the SAME peer and
+        # NCCL matches the sends and receives of a pair in order
+        ops = [dist.P2POp(dist.isend, send_r, right, group=self.group), dist.P2POp(dist.isend, send_l, left, group=self.group),
+               dist.P2POp(dist.irecv, recv_l, left, group=self.group), dist.P2POp(dist.irecv, recv_r, right, group=self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    def rebuild_local(self) -> None:
+        """Slab-local rebuild after a halt (include/ljmd.h, ljmd_ctx_slab_rebuild_local)."""
+        dist, ctx, cap = self.dist, self.ctx, self.halo_cap
+        send_l, send_r, recv_l, recv_r = self.halo
+        with self.torch.cuda.stream(self.stream):
+            ctx.slab_halo(send_l.data_ptr(), cap, 0, False)   # my first two cell layers, for the left neighbour
+            ctx.slab_halo(send_r.data_ptr(), cap, 1, False)   # my last two, for the right neighbour
+            self._exchange_halos()
+            ctx.slab_halo(recv_l.data_ptr(), cap, 0, True)
+            ctx.slab_halo(recv_r.data_ptr(), cap, 1, True)
+            ctx.slab_rebuild_local(0)
+            dist.all_reduce(self.hist, group=self.group)      # every rank counted the cells of its own layers
+            ctx.slab_rebuild_local(1)
 
     def step(self, nsteps: int) -> np.ndarray:
         """nsteps velocity-Verlet steps; returns this rank's observable share of the last step."""
@@ -180,12 +226,16 @@ class SlabRunner:
                 shadow = os.environ.get("LJMD_SLAB_SHADOW")
                 if shadow:
                     d0 = self.ctx.download(("vx", "ax", "ay"))
-                self.gather()
-                self.stream.synchronize()
-                t2 = time.perf_counter()
-                self.ctx.slab_rebuild()
+                if self.local:
+                    t2 = time.perf_counter()
+                    self.rebuild_local()
+                else:
+                    self.gather()
+                    self.stream.synchronize()
+                    t2 = time.perf_counter()
+                    self.ctx.slab_rebuild()
+                    self.bounds = self.ctx.slab_bounds()
                 self.rebuilds += 1
-                self.bounds = self.ctx.slab_bounds()
                 if shadow:
                     d1 = self.ctx.download(("vx", "ax", "ay"))
                     for nm in ("vx", "ax", "ay"):
@@ -209,14 +259,15 @@ class SlabRunner:
 
     def finish(self) -> None:
         """Leave the complete, current state on every rank (for download)."""
+        self.bounds = self.ctx.slab_bounds()
         self.gather()
 
 
 class DeviceArray:
     """Wraps a raw device address so that torch.as_tensor(...) views it without a copy."""
 
-    def __init__(self, ptr: int, nelem: int):
-        self.__cuda_array_interface__ = {"shape": (nelem,), "typestr": "<f8", "data": (ptr, False),
+    def __init__(self, ptr: int, nelem: int, typestr: str = "<f8"):
+        self.__cuda_array_interface__ = {"shape": (nelem,), "typestr": typestr, "data": (ptr, False),
                                          "version": 3}
 
 
