@@ -277,11 +277,11 @@ def measure_single(lj, wname, steps, warmup, local, seed=0, e2e_steps=20, cpu_bu
 
     # ---- device-resident timing: W warm-up steps, then exactly K steps ----------------------
     ctx.step(warmup)
-    if barrier:
-        barrier()
     reb0 = ctx.nlist_info()["rebuilds"] if w["method"] == "nlist" else 0
     sampler = ClockSampler(local)
     sampler.start()
+    if barrier:
+        barrier()
     l0 = ctx.launch_count
     t0 = time.perf_counter()
     obs = ctx.step(steps)  # graphs are prepared before the first event; returns after a stream synchronize
@@ -415,10 +415,13 @@ def run_slabs(args, w, lj, mg, dist, rank, world, local, n, arrs, p):
     ctx.compute_forces()
     runner = mg.SlabRunner(ctx, rank, world, chunk=32)
     runner.step(args.warmup)
-    torch.cuda.synchronize()
-    dist.barrier()
+    runner.prepare(args.steps)  # graphs of the timed region, like ljmd_ctx_step prepares its own before the first event
+    # the sampler thread (NVML initialisation: milliseconds, different on every rank) starts BEFORE the barrier:
+    # whatever a rank does between the barrier and its first launch is waited for by all the others
     sampler = ClockSampler(local)
     sampler.start()
+    torch.cuda.synchronize()
+    dist.barrier()
     l0, r0, d0 = ctx.launch_count, runner.rebuilds, runner.t_run_dev_ms
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()

@@ -239,6 +239,9 @@ int ljmd_ctx_slab_local_info(ljmd_ctx *ctx, uint64_t *cell_count_ptr, int32_t *n
                              int32_t *halo_narr);
 int ljmd_ctx_slab_halo(ljmd_ctx *ctx, double *dev_buf, int32_t cap, int32_t side, int32_t unpack);
 int ljmd_ctx_slab_rebuild_local(ljmd_ctx *ctx, int32_t phase);
+/* Captures the CUDA graph that ljmd_ctx_slab_run replays for a chunk of max_steps (2 .. 32) steps now, so that the
+ * first run of that length does not pay for the capture.  Optional. */
+int ljmd_ctx_slab_prepare(ljmd_ctx *ctx, int32_t max_steps);
 
 /* Self-check of the neighbour-list path: total momentum (sum of v) of the atoms handled by the last
  * step launch -- an invariant of the dynamics (a sharded run adds the ranks' shares). */

@@ -92,6 +92,7 @@ ABI_SYMBOLS = [
     "ljmd_ctx_slab_export", "ljmd_ctx_slab_attach", "ljmd_ctx_slab_bounds", "ljmd_ctx_slab_pack",
     "ljmd_ctx_slab_unpack", "ljmd_ctx_slab_drift", "ljmd_ctx_slab_rebuild", "ljmd_ctx_slab_run",
     "ljmd_ctx_slab_poison", "ljmd_ctx_slab_local_info", "ljmd_ctx_slab_halo", "ljmd_ctx_slab_rebuild_local",
+    "ljmd_ctx_slab_prepare",
     "ljmd_ctx_series_arm", "ljmd_ctx_series_fetch",
     "ljmd_ctx_nlist_momentum", "ljmd_rdf_histogram", "ljmd_time_correlation",
 ]
@@ -499,6 +500,9 @@ class Context:
 
     def slab_halo(self, dev_ptr: int, cap: int, side: int, unpack: bool) -> None:
         _chk(self._L.ljmd_ctx_slab_halo(self._h, C.c_void_p(dev_ptr), int(cap), int(side), 1 if unpack else 0))
+
+    def slab_prepare(self, max_steps: int) -> None:
+        _chk(self._L.ljmd_ctx_slab_prepare(self._h, int(max_steps)))
 
     def slab_rebuild_local(self, phase: int) -> None:
         _chk(self._L.ljmd_ctx_slab_rebuild_local(self._h, int(phase)))

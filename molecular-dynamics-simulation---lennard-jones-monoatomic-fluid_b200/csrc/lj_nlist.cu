@@ -713,7 +713,7 @@ __device__ __forceinline__ void nl_st_release_sys(int *p, int v)
 #define LJMD_NL_THREADS_SH 1024 // 8 CTAs per SM: the 1050 CTAs of the fullest rank of an 8-GPU run at N = 2^20 are ONE wave
 #endif
 #ifndef LJMD_NL_PUBLISH_IN_KERNEL
-#define LJMD_NL_PUBLISH_IN_KERNEL 0 // 1: the last CTA of a sharded step publishes the flags itself
+#define LJMD_NL_PUBLISH_IN_KERNEL 1 // the last CTA of a sharded step publishes the flags itself (0: a 1-warp kernel after every step)
 #endif
 #ifndef LJMD_NL_THREADS_STEP
 #define LJMD_NL_THREADS_STEP 1024
@@ -913,21 +913,40 @@ nl_step_kernel(NlArgs a)
     // 8192 CTAs it was 25 us of a 294 us kernel -- the adds keep their order, so the sums are unchanged bit for bit)
     double r[NL_NS] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const int nrow = SH ? nact : (int)gridDim.x;
-    int b = threadIdx.x;
-    for (; b + 3 * NL_BS < nrow; b += 4 * NL_BS) {
+    // thread 0 needs two more values at the very end; their round trips overlap with the reduction
+    long long step_pre = 0;
+    unsigned long long maxd2_pre = 0ull;
+    if (MODE == 1 && threadIdx.x == 0) {
+        step_pre = *((volatile long long *)&a.sctl->step);
+        maxd2_pre = *((volatile unsigned long long *)&a.ctl->maxd2_bits); // final: every CTA folded its maximum in before its ticket
+    }
+#if LJMD_NL_PUBLISH_IN_KERNEL
+    if (SH && MODE == 1 && threadIdx.x < 32) {
+        // Publish "step seq+1 done (+ skin violated)" to every rank NOW, before the scalar reduction below: all the
+        // flag says is that every CTA of this rank has taken its ticket (so every halo position was fenced
+        // system-wide before) and whether the skin was violated; the peers' next kernels then never wait for this
+        // rank's bookkeeping.  One lane per peer: world release stores issued by one thread would queue up
+        // behind each other's round trips.
+        const unsigned long long mb = __shfl_sync(0xffffffffu, maxd2_pre, 0);
+        const int flag_val = ((seq + 1) << 1) | (__longlong_as_double((long long)mb) > a.half_skin2 ? 1 : 0);
+        if ((int)threadIdx.x < a.world)
+            nl_st_release_sys(a.peer_flags[threadIdx.x] + ((seq + 1) & 1) * LJMD_MAX_RANKS + a.rank, flag_val);
+    }
+#endif
+    for (int b = threadIdx.x; b < nrow; b += 4 * NL_BS) {
         double v[4][NL_NS];
 #pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int row = b + u * NL_BS;
+#pragma unroll
+            for (int q = 0; q < NL_NS; ++q) v[u][q] = row < nrow ? __ldcg(a.spart + (size_t)row * NL_NS + q) : 0.0;
+        }
+#pragma unroll
         for (int u = 0; u < 4; ++u)
+            if (b + u * NL_BS < nrow) {
 #pragma unroll
-            for (int q = 0; q < NL_NS; ++q) v[u][q] = __ldcg(a.spart + (size_t)(b + u * NL_BS) * NL_NS + q);
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int q = 0; q < NL_NS; ++q) r[q] += v[u][q];
-    }
-    for (; b < nrow; b += NL_BS) {
-#pragma unroll
-        for (int q = 0; q < NL_NS; ++q) r[q] += __ldcg(a.spart + (size_t)b * NL_NS + q);
+                for (int q = 0; q < NL_NS; ++q) r[q] += v[u][q];
+            }
     }
     block_sum<NL_NS>(r, scratch);
     if (threadIdx.x == 0) {
@@ -942,7 +961,7 @@ nl_step_kernel(NlArgs a)
         a.obs[0] = o[0]; a.obs[1] = o[1]; a.obs[2] = o[2]; a.obs[3] = o[3];
         if (MODE == 1) {
             StepCtl *sc = a.sctl;
-            const long long step = sc->step;
+            const long long step = step_pre;
             if (sc->series && step < sc->series_cap) {
                 double *sr = sc->series + (size_t)step * 4;
                 sr[0] = o[0]; sr[1] = o[1]; sr[2] = o[2]; sr[3] = o[3];
@@ -950,16 +969,14 @@ nl_step_kernel(NlArgs a)
             sc->step = step + 1;
             a.ctl->cur = 1 - cur;
             a.ctl->unwrapped = 0; // every position the next step reads has been wrapped
-            const double m = __longlong_as_double((long long)a.ctl->maxd2_bits);
+            const double m = __longlong_as_double((long long)maxd2_pre);
             if (!SH) {
                 if (m > a.half_skin2) a.ctl->need_rebuild = 1;
             } else {
                 // "step seq+1 done (+ skin violated)": published to every rank by nl_publish_kernel
                 const int flag_val = ((seq + 1) << 1) | (m > a.half_skin2 ? 1 : 0);
                 a.ctl->pending_flag = flag_val;
-#if LJMD_NL_PUBLISH_IN_KERNEL
-                s_flag = flag_val; // published below by one lane per peer
-#endif
+
                 a.ctl->seq = seq + 1;
                 a.ctl->steps_left -= 1;
                 a.ctl->steps_done += 1;
@@ -968,17 +985,6 @@ nl_step_kernel(NlArgs a)
         a.ctl->ticket_step = 0;
         if (SH && a.dbg_time && seq < 1024) a.dbg_time[4 * seq + 3] = nl_globaltimer();
     }
-#if LJMD_NL_PUBLISH_IN_KERNEL
-    if (SH && MODE == 1) {
-        // Publish "step seq+1 done (+ skin violated)" from here and save one launch per step.  Every thread that
-        // pushed halo positions fenced them system-wide before its CTA took the ticket and this CTA saw all
-        // tickets, so the release stores below order them.  One lane per peer: world release stores issued by
-        // one thread would queue up behind each other's round trips.
-        __syncthreads();
-        if ((int)threadIdx.x < a.world)
-            nl_st_release_sys(a.peer_flags[threadIdx.x] + ((seq + 1) & 1) * LJMD_MAX_RANKS + a.rank, s_flag);
-    }
-#endif
 }
 
 // First step of a run: rb[1-cur] = wrap(drift(rb[cur], v, a)) (verlet.f90:58-63) + skin check.
@@ -1885,9 +1891,51 @@ extern "C" int ljmd_ctx_slab_rebuild_local(ljmd_ctx *c, int32_t phase)
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) rc = set_error(LJMD_ERR_CUDA, "ljmd_ctx_slab_rebuild_local(): %s", cudaGetErrorString(e));
-    if (rc == LJMD_OK && phase != 0) rc = nlist_check_overflow(c);
+    // no host synchronisation here: a list overflow of this build is reported by the next ljmd_ctx_slab_run
+    // (its step kernels are no-ops once the flag is set), so the host can queue the next chunk at once
     if (prev != c->device) cudaSetDevice(prev);
     return rc;
+}
+
+// Captures the CUDA graph of a chunk of max_steps (2 .. 32) sharded steps now, so that the first
+// ljmd_ctx_slab_run of that length does not pay for it.
+extern "C" int ljmd_ctx_slab_prepare(ljmd_ctx *c, int32_t max_steps)
+{
+    clear_error();
+    if (!c) return set_error(LJMD_ERR_NULL, "ljmd_ctx_slab_prepare(): ctx is NULL.");
+    if (!c->nw.sh_on) return set_error(LJMD_ERR_ARG, "ljmd_ctx_slab_prepare(): context is not sharded.");
+    const char *ge = getenv("LJMD_SLAB_GRAPH");
+    if (max_steps < 2 || max_steps > 32 || (ge && atoi(ge) == 0) || c->graph_slab[max_steps]) return LJMD_OK;
+    int prev = 0;
+    LJMD_CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != c->device) LJMD_CUDA_CHECK(cudaSetDevice(c->device));
+    NlistWork &w = c->nw;
+    const int cur_save = w.cur_host;
+    int rc = LJMD_OK;
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+        c->capturing = true;
+        for (int s = 0; s < max_steps && rc == LJMD_OK; ++s) {
+            rc = nlist_enqueue_step_kernel(c);
+#if !LJMD_NL_PUBLISH_IN_KERNEL
+            if (rc == LJMD_OK) {
+                const NlArgs a = make_args(c, 0);
+                nl_publish_kernel<<<1, 32, 0, c->stream>>>(a);
+            }
+#endif
+        }
+        c->capturing = false;
+        const cudaError_t e2 = cudaStreamEndCapture(c->stream, &g);
+        if (e2 != cudaSuccess) e = e2;
+    }
+    w.cur_host = cur_save; // capture executes nothing
+    if (e == cudaSuccess && rc == LJMD_OK) e = cudaGraphInstantiate(&c->graph_slab[max_steps], g, 0);
+    if (g) cudaGraphDestroy(g);
+    if (prev != c->device) cudaSetDevice(prev);
+    if (rc != LJMD_OK) return rc;
+    if (e != cudaSuccess) return set_error(LJMD_ERR_CUDA, "ljmd_ctx_slab_prepare(): %s", cudaGetErrorString(e));
+    return LJMD_OK;
 }
 
 // Total momentum (sum of v over the atoms the last step / force launch of this context handled).
@@ -2044,7 +2092,7 @@ extern "C" int ljmd_ctx_slab_run(ljmd_ctx *c, int32_t max_steps, int32_t *steps_
         }
     };
     if (use_graph && e == cudaSuccess) {
-        if (!c->graph_slab[max_steps]) {
+        if (!c->graph_slab[max_steps]) { // normally captured ahead of time by ljmd_ctx_slab_prepare
             const int cur_save = w.cur_host;
             cudaGraph_t g = nullptr;
             e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
@@ -2087,6 +2135,7 @@ extern "C" int ljmd_ctx_slab_run(ljmd_ctx *c, int32_t max_steps, int32_t *steps_
     if (prev != c->device) cudaSetDevice(prev);
     if (e != cudaSuccess) return set_error(LJMD_ERR_CUDA, "ljmd_ctx_slab_run(): %s", cudaGetErrorString(e));
     if (rc != LJMD_OK) return rc;
+    w.rebuilds_host = h.rebuilds;
     // the host mirror of cur follows the steps that really ran
     if (((max_steps - h.steps_done) & 1) != 0) w.cur_host ^= 1;
     *steps_done = h.steps_done;

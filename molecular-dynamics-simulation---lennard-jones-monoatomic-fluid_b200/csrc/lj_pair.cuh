@@ -1,9 +1,17 @@
 // lj_pair.cuh -- the per-pair arithmetic shared by every force kernel.
 //
-// Compiled with -fmad=false.  Each per-pair quantity is computed with exactly the operations,
-// operand order and roundings of the reference loop body
-// (/root/reference/scripts/physics/lj_potential_energy.f90:119-178), so the terms that are
-// summed are bit-identical to the reference's; only the ORDER of the sums differs.
+// Compiled with -fmad=false.  What is bit-identical to the reference loop body
+// (/root/reference/scripts/physics/lj_potential_energy.f90:119-178) and what is not:
+//   * mic(), dist2(): the reference's operations, operand order and roundings -- r2 and therefore the
+//     cutoff decision r2 < rc2 (:132) are the reference's, for every pair, in every kernel.
+//   * pair_terms() (full-matrix cross-check kernel, plain cell list): IEEE division and the reference's
+//     operation order -- every summed term is bit-identical; only the ORDER of the sums differs.
+//   * the default kernels (symmetric all-pairs tiles, neighbour-list walk) do NOT use pair_terms(): they
+//     take 1/r2 from MUFU.RCP64H + one cubic step (<= 1 ulp, not correctly rounded), accumulate forces with
+//     explicit FMAs and sum r^-12 and r^-6 separately (U, d_epot, dd_epot are formed from the two sums at
+//     the end).  Their per-pair terms agree with the reference's to ~1 ulp, the results to ~1e-15 relative;
+//     the tests hold them to 1e-12 (forces per atom against the sum of the pair-force magnitudes).
+// The checker is the C restatement in oracle/ (same author; no Fortran compiler here, parity unpinned).
 #pragma once
 #include <cuda_runtime.h>
 

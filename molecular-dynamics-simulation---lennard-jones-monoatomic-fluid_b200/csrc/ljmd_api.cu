@@ -952,6 +952,38 @@ namespace {
 std::mutex g_compat_mu;
 ljmd_ctx *g_compat = nullptr;
 
+// Page-locking of the CALLER's arrays (large systems only): the drop-in pair is called with the same nine
+// allocatable arrays for a whole run (md_simulation_program.f90:216-222 allocates them once), so they are
+// registered with the driver at the first call and the H2D / D2H copies then go straight from / to them -- no
+// staging memcpy through a pinned bounce buffer (two passes over 75 MB each at N = 2^20: 60 % of the call).
+// The registrations are dropped by ljmd_compat_release(), which a host must call BEFORE it frees arrays it has
+// passed in; LJMD_COMPAT_PIN=0 turns the feature off.  Small arrays keep the bounce buffer.
+struct PinnedRange { const void *p; size_t bytes; };
+std::vector<PinnedRange> g_pinned;
+const size_t kPinMinBytes = (size_t)1 << 20;
+
+bool compat_pin(const void *p, size_t bytes)
+{
+    static const bool enabled = !(getenv("LJMD_COMPAT_PIN") && atoi(getenv("LJMD_COMPAT_PIN")) == 0);
+    if (!enabled || bytes < kPinMinBytes) return false;
+    for (const PinnedRange &r : g_pinned)
+        if (r.p == p && r.bytes >= bytes) return true;
+    if (g_pinned.size() >= 64) return false;
+    if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) != cudaSuccess) {
+        cudaGetLastError(); // e.g. already registered by the caller with another size: use the bounce buffer
+        return false;
+    }
+    g_pinned.push_back({p, bytes});
+    return true;
+}
+
+void compat_unpin_all()
+{
+    for (const PinnedRange &r : g_pinned) cudaHostUnregister(const_cast<void *>(r.p));
+    cudaGetLastError();
+    g_pinned.clear();
+}
+
 int compat_ctx(const ljmd_params *p, const char *who, ljmd_ctx **out)
 {
     LJMD_TRY(check_params(p, who));
@@ -980,7 +1012,13 @@ int compat_ctx(const ljmd_params *p, const char *who, ljmd_ctx **out)
 extern "C" int ljmd_compat_release(void)
 {
     std::lock_guard<std::mutex> lk(g_compat_mu);
-    if (g_compat) { ljmd_ctx_destroy(g_compat); g_compat = nullptr; }
+    if (g_compat) {
+        cudaStreamSynchronize(g_compat->stream);
+        compat_unpin_all();
+        ljmd_ctx_destroy(g_compat);
+        g_compat = nullptr;
+    }
+    compat_unpin_all();
     return LJMD_OK;
 }
 
@@ -1001,6 +1039,32 @@ extern "C" int ljmd_compute_lj(const ljmd_params *params, const double *rx, cons
     LJMD_TRY(g.enter(c->device));
     LJMD_TRY(ensure_stage(c));
     const size_t nb = sizeof(double) * c->nR;
+    const double *in3[3] = {rx, ry, rz};
+    double *out3[3] = {ax, ay, az};
+    bool direct = true;
+    for (int k = 0; k < 3; ++k) direct = compat_pin(in3[k], nb) && direct;
+    for (int k = 0; k < 3; ++k) direct = compat_pin(out3[k], nb) && direct;
+    if (direct) {
+        for (int k = 0; k < 3; ++k)
+            LJMD_CUDA_CHECK(cudaMemcpyAsync(c->st.rx + (size_t)k * c->nR, in3[k], nb, cudaMemcpyHostToDevice, c->stream));
+        const double *dev_acc = c->st.ax;
+        if (c->method == LJMD_METHOD_NLIST) {
+            LJMD_TRY(nlist_reset_identity(c));
+            LJMD_TRY(nlist_enqueue_forces(c));
+            LJMD_TRY(nlist_gather_orig(c)); // accelerations back in original order
+            dev_acc = c->nw.alt + 6 * c->nR;
+        } else {
+            LJMD_TRY(enqueue_force(c, 0));
+            LJMD_TRY(launch_finalize(c, 0, 0, 0, 0));
+        }
+        for (int k = 0; k < 3; ++k)
+            LJMD_CUDA_CHECK(cudaMemcpyAsync(out3[k], dev_acc + (size_t)k * c->nR, nb, cudaMemcpyDeviceToHost, c->stream));
+        LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_obs, c->fw.obs, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
+        LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        *epot = c->h_obs[0]; *d_epot = c->h_obs[2]; *dd_epot = c->h_obs[3];
+        if (c->method == LJMD_METHOD_NLIST) LJMD_TRY(nlist_check_overflow(c));
+        return LJMD_OK;
+    }
     memcpy(c->h_stage, rx, nb);
     memcpy(c->h_stage + c->nR, ry, nb);
     memcpy(c->h_stage + 2 * c->nR, rz, nb);
@@ -1049,6 +1113,30 @@ extern "C" int ljmd_verlet_step(const ljmd_params *params, double *rx, double *r
     LJMD_TRY(ensure_stage(c));
     const size_t nb = sizeof(double) * c->nR;
     double *arr[9] = {rx, ry, rz, vx, vy, vz, ax, ay, az};
+    bool direct = true; // large arrays: copy straight from / to the caller's (now page-locked) arrays
+    for (int k = 0; k < 9; ++k) direct = compat_pin(arr[k], nb) && direct;
+    if (direct) {
+        for (int k = 0; k < 9; ++k)
+            LJMD_CUDA_CHECK(cudaMemcpyAsync(c->state_block + (size_t)k * c->nR, arr[k], nb, cudaMemcpyHostToDevice, c->stream));
+        const double *dev_src = c->state_block;
+        if (c->method == LJMD_METHOD_NLIST) {
+            LJMD_TRY(nlist_reset_identity(c));
+            LJMD_TRY(nlist_enqueue_drift(c));
+            LJMD_TRY(nlist_enqueue_step(c));
+            LJMD_TRY(nlist_gather_orig(c)); // r(t+dt), v, a back in original order
+            dev_src = c->nw.alt;
+        } else {
+            LJMD_TRY(launch_drift(c, 0, 1));
+            LJMD_TRY(enqueue_step(c, 0, 2));
+        }
+        for (int k = 0; k < 9; ++k)
+            LJMD_CUDA_CHECK(cudaMemcpyAsync(arr[k], dev_src + (size_t)k * c->nR, nb, cudaMemcpyDeviceToHost, c->stream));
+        LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_obs, c->fw.obs, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
+        LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (c->method == LJMD_METHOD_NLIST) LJMD_TRY(nlist_check_overflow(c));
+        *epot = c->h_obs[0]; *ekin = c->h_obs[1]; *d_epot = c->h_obs[2]; *dd_epot = c->h_obs[3];
+        return LJMD_OK;
+    }
     for (int k = 0; k < 9; ++k) memcpy(c->h_stage + (size_t)k * c->nR, arr[k], nb);
     // Upload, drift, force, finalize and download replayed as ONE graph launch instead of two copies
     // and three kernel launches (bitwise equal to the separate launches, tests/test_gpu_parity.py;

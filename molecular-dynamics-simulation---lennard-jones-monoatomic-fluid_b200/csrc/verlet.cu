@@ -93,7 +93,9 @@ struct FinArgs {
     StepCtl *ctl;
 };
 
-template <int G>
+// SORTED: the spatially sorted all-pairs kernel produced the partials (flagged j-side partials, thousands of scalar
+// partials); a separate instantiation so that the small-system path keeps its lean code.
+template <int G, bool SORTED = false>
 __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
 {
     constexpr int APB = 256 / G; // atoms per CTA
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
             const double *fj = a.sym ? a.fJ + (size_t)rep * a.n_rows * 3 * n : nullptr;
             const double *fp = a.fpart + (size_t)rep * a.n_splits * 3 * n;
             const int P = nj + nsp;
-            if (!a.near) {
+            if (!SORTED) {
 #pragma unroll 4
                 for (int p = g; p < P; p += G) {
                     const double *src = (p < nj) ? fj + (size_t)p * 3 * n : fp + (size_t)(p - nj) * 3 * n;
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
             }
         }
     }
-    if (G == 8 && a.near) {
+    if (G == 8 && SORTED) {
         // Sorted all-pairs kernel: only the (row, chunk) tiles that held an in-cutoff pair wrote a j-side
         // partial; near[chunk][row] says which.  APB = 32: this CTA is ONE chunk and warp g = group g.  The
         // warp reads the flags of 32 rows with one coalesced load, and walks the set bits in ascending row
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a)
     // (fixed shape => bit-reproducible).  One CTA walking all of them alone was the tail of this kernel: 19 k
     // work items at N = 32k cost it 60 us.
     double sl[3] = {0.0, 0.0, 0.0};
-    const bool two_level = a.n_spart > 1024; // few partials (small systems): the last CTA reads them directly, as before
+    const bool two_level = SORTED; // few partials (small systems): the last CTA reads them directly, as before
     if (two_level) {
         const int S = (a.n_spart + (int)gridDim.x - 1) / (int)gridDim.x;
         const int b0 = blockIdx.x * S, b1 = min(a.n_spart, b0 + S);
@@ -345,7 +347,8 @@ int launch_finalize(ljmd_ctx *c, int mode, int prev, int now, int out)
     a.ctl = c->fw.ctl;
     const int apb = 256 / c->fw.groups;
     dim3 grid(c->sharded ? (a.i_end - a.i_begin + apb - 1) / apb : c->fw.nblk, c->R);
-    if (c->fw.groups == 8) finalize_kernel<8><<<grid, 256, 0, c->stream>>>(a);
+    if (c->fw.groups == 8 && a.near) finalize_kernel<8, true><<<grid, 256, 0, c->stream>>>(a);
+    else if (c->fw.groups == 8) finalize_kernel<8><<<grid, 256, 0, c->stream>>>(a);
     else finalize_kernel<1><<<grid, 256, 0, c->stream>>>(a);
     if (!c->capturing) c->launches++;
     LJMD_CUDA_CHECK(cudaGetLastError());

@@ -196,6 +196,13 @@ class SlabRunner:
             dist.all_reduce(self.hist, group=self.group)      # every rank counted the cells of its own layers
             ctx.slab_rebuild_local(1)
 
+    def prepare(self, nsteps: int) -> None:
+        """Captures the CUDA graphs step(nsteps) will replay (chunks of `chunk` steps and the remainder) ahead of
+        time.  A halt in the middle of a chunk leaves an odd-sized remainder whose graph is captured when it occurs."""
+        for m in {min(self.chunk, nsteps), nsteps % self.chunk}:
+            if m >= 2:
+                self.ctx.slab_prepare(m)
+
     def step(self, nsteps: int) -> np.ndarray:
         """nsteps velocity-Verlet steps; returns this rank's observable share of the last step."""
         left = nsteps

@@ -49,3 +49,35 @@ def test_compat_graph_is_bitwise_equal_to_the_default_drop_in_call(tmp_path):
     b = _run(tmp_path, "graph", {})
     assert np.array_equal(a["obs"], b["obs"])
     assert np.array_equal(a["state"], b["state"])
+
+
+_SCRIPT_BIG = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+import bench, ljmd_b200 as lj
+k = 32                                             # N = 131,072: 1 MiB per array, the page-locking threshold
+L = k * (4.0 / 0.8) ** (1.0 / 3.0)
+w = dict(k=k, L=L, rc=2.5, dt=1e-3, method="nlist", T=1.0)
+n, arrs = bench.synthetic_state(w, seed=9)
+p = lj.init_params(n, L, 1e-3, 2.5, k)
+s = lj.SimState.from_arrays(arrs)
+e0 = lj.compute_lj_potential_energy(p, s)
+obs = [lj.verlet_step(p, s) for _ in range(3)]
+lj.compat_release()                                # before the arrays go away
+np.savez(sys.argv[1], state=np.array([getattr(s, nm) for nm in lj.SimState.NAMES]), obs=np.array(obs), e0=np.array(e0))
+"""
+
+
+def test_page_locked_caller_arrays_are_bitwise_equal_to_the_bounce_buffer(tmp_path):
+    """Large systems: the drop-in pair page-locks the caller's arrays and copies straight from / to them
+    (LJMD_COMPAT_PIN=0: pinned bounce buffer + two memcpy passes).  Same results, bit for bit."""
+    outs = []
+    for name, env_extra in (("bounce", {"LJMD_COMPAT_PIN": "0"}), ("pinned", {})):
+        out = tmp_path / (name + ".npz")
+        env = dict(os.environ)
+        env.pop("LJMD_COMPAT_PIN", None)
+        env.update(env_extra)
+        subprocess.run([sys.executable, "-c", _SCRIPT_BIG.format(root=ROOT), str(out)], check=True, env=env, timeout=240)
+        outs.append(np.load(out))
+    for key in ("obs", "state", "e0"):
+        assert np.array_equal(outs[0][key], outs[1][key]), key
