@@ -11,7 +11,7 @@
 //     explicit FMAs and sum r^-12 and r^-6 separately (U, d_epot, dd_epot are formed from the two sums at
 //     the end).  Their per-pair terms agree with the reference's to ~1 ulp, the results to ~1e-15 relative;
 //     the tests hold them to 1e-12 (forces per atom against the sum of the pair-force magnitudes).
-// The checker is the C restatement in oracle/ (same author; no Fortran compiler here, parity unpinned).
+// The checker is a CPU restatement of the reference by the same author (no Fortran compiler here: parity unpinned).
 #pragma once
 #include <cuda_runtime.h>
 
