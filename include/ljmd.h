@@ -203,8 +203,9 @@ int ljmd_tail_corrections(const ljmd_params *params, double *tail_epot, double *
  * boundary layers straight into the neighbour ranks' position buffers (peer memory over NVLink)
  * and publishes a per-step flag to every rank; the next step starts when all flags have arrived
  * (no host round trip, no NCCL call per step).  A skin violation on any rank halts all ranks at
- * the same step; the host then gathers the complete state (one NCCL all-gather of the packed
- * slabs), and every rank re-sorts and rebuilds the lists of its own slab.
+ * the same step; the host then rebuilds the lists: slab-locally (ljmd_ctx_slab_halo / _rebuild_local below: two cell
+ * layers exchanged with each neighbour, one all-reduce of the cell histogram) or globally (one NCCL all-gather of
+ * the packed slabs, ljmd_ctx_slab_pack / _unpack, then ljmd_ctx_slab_rebuild re-sorts everything on every rank).
  *   export  : 128 bytes = two cudaIpcMemHandle_t (position buffers, flag block) and/or the raw
  *             device pointers (for contexts living in the same process)
  *   attach  : all_handles = world x 128 bytes in rank order (or all_raw_ptrs = world x 2) */
@@ -214,7 +215,8 @@ int ljmd_ctx_slab_attach(ljmd_ctx *ctx, int32_t rank, int32_t world, const void 
                          const uint64_t *all_raw_ptrs);
 /* First slot of every rank's slab in the current sorted order; bounds[world] = n. */
 int ljmd_ctx_slab_bounds(ljmd_ctx *ctx, int32_t *bounds);
-/* Owned range of every state array -> dense device buffer [narr][cmax] (dev_buf NULL: query narr). */
+/* Owned range of every state array and the original atom indices -> dense device buffer [narr][cmax]
+ * (narr = state arrays + 1; dev_buf NULL: query narr). */
 int ljmd_ctx_slab_pack(ljmd_ctx *ctx, double *dev_buf, int32_t cmax, int32_t *narr);
 /* All ranks' packed ranges [world][narr][cmax] -> state arrays: the complete state on this rank. */
 int ljmd_ctx_slab_unpack(ljmd_ctx *ctx, const double *dev_buf, int32_t cmax);
@@ -223,7 +225,9 @@ int ljmd_ctx_slab_drift(ljmd_ctx *ctx);
 /* Global re-sort + list rebuild for the next step's positions (needs the complete state) if a
  * halt / the skin check asked for it or force != 0; clears the halt. */
 int ljmd_ctx_slab_rebuild(ljmd_ctx *ctx, int32_t force);
-/* Up to max_steps steps; *halted != 0 => gather (pack / all-gather / unpack) + rebuild, then go on.
+/* Up to max_steps steps (<= 32 of them are replayed as one CUDA graph); *halted != 0 => rebuild the lists (locally or
+ * globally, see above), then go on.  A neighbour-list overflow or a peer whose flag never arrives (bounded wait) is
+ * reported here as an error, with the state frozen at the last completed step.
  * obs4 = this rank's share of {epot, ekin, d_epot, dd_epot} of the last step, no tail corrections. */
 int ljmd_ctx_slab_run(ljmd_ctx *ctx, int32_t max_steps, int32_t *steps_done, int32_t *halted,
                       double *obs4);

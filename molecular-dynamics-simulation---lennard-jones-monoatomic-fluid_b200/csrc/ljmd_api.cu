@@ -159,6 +159,46 @@ static void stage_out(const ljmd_ctx *c, double *dst, const double *src)
     else memcpy(dst, src, sizeof(double) * n);
 }
 
+// Re-sort of a spatially sorted all-pairs context between two steps (positions in rbuf[0]): diffusion slowly
+// loosens the chunk boxes the kernel's per-tile tests rely on (it stays correct, more tiles fall back to the
+// general path).  Host-side like the first sort: D2H of the state, new order from the current positions, H2D.
+// The resident order is not observable (upload / download translate), the sums change order: results move by
+// rounding only, and WHEN it happens depends on the step count since the last complete upload alone.
+static int resort_allpairs(ljmd_ctx *c)
+{
+    const size_t n = c->nR, nb = sizeof(double) * n;
+    const int narr = c->st.rux ? 12 : 9;
+    std::vector<double> host((size_t)narr * n), tmp(n);
+    LJMD_CUDA_CHECK(cudaMemcpyAsync(host.data(), c->state_block, 9 * nb, cudaMemcpyDeviceToHost, c->stream));
+    if (c->st.rux) LJMD_CUDA_CHECK(cudaMemcpyAsync(host.data() + 9 * n, c->st.rux, 3 * nb, cudaMemcpyDeviceToHost, c->stream));
+    LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    std::vector<int> idx(n), newperm(n);
+    std::iota(idx.begin(), idx.end(), 0);
+    kd_order_rec(idx.data(), (int)n, host.data(), host.data() + n, host.data() + 2 * n); // new slot k <- old slot idx[k]
+    for (size_t k = 0; k < n; ++k) newperm[k] = c->pw.perm ? c->pw.perm[idx[k]] : idx[k];
+    if (!c->pw.perm) {
+        c->pw.perm = (int *)malloc(sizeof(int) * n);
+        if (!c->pw.perm) return set_error(LJMD_ERR_NOMEM, "out of host memory (sort permutation).");
+    }
+    memcpy(c->pw.perm, newperm.data(), sizeof(int) * n);
+    for (int a = 0; a < narr; ++a) {
+        double *arr = host.data() + (size_t)a * n;
+        for (size_t k = 0; k < n; ++k) tmp[k] = arr[idx[k]];
+        memcpy(arr, tmp.data(), nb);
+    }
+    LJMD_CUDA_CHECK(cudaMemcpyAsync(c->state_block, host.data(), 9 * nb, cudaMemcpyHostToDevice, c->stream));
+    if (c->st.rux) LJMD_CUDA_CHECK(cudaMemcpyAsync(c->st.rux, host.data() + 9 * n, 3 * nb, cudaMemcpyHostToDevice, c->stream));
+    LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream)); // `host` goes out of scope
+    c->pw.steps_since_sort = 0;
+    return LJMD_OK;
+}
+
+static long long sort_interval()
+{
+    const char *e = getenv("LJMD_SORT_INTERVAL"); // steps between re-sorts; <= 0: never
+    return e ? atoll(e) : 2000;
+}
+
 static int enqueue_force(ljmd_ctx *c, int buf)
 {
     if (c->method == LJMD_METHOD_CELLS) return launch_cells_force(c, buf);
@@ -275,10 +315,31 @@ static int prepare_graphs(ljmd_ctx *c, int nsteps)
     return LJMD_OK;
 }
 
+static int run_steps_segment(ljmd_ctx *c, int nsteps);
+static int prepare_graphs(ljmd_ctx *c, int nsteps);
+
 static int run_steps(ljmd_ctx *c, int nsteps)
 {
     if (nsteps <= 0) return LJMD_OK;
     if (c->method == LJMD_METHOD_NLIST) return run_steps_nlist(c, nsteps);
+    const long long iv = sort_interval();
+    if (c->method != LJMD_METHOD_ALLPAIRS || !c->pw.sorted || iv <= 0 || c->R != 1) return run_steps_segment(c, nsteps);
+    // sorted all-pairs: segments that end at the re-sort points (multiples of the interval since the last complete upload)
+    int left = nsteps;
+    while (left > 0) {
+        const long long room = iv - c->pw.steps_since_sort;
+        const int todo = (int)std::min<long long>(left, room > 0 ? room : iv);
+        if (todo != nsteps) LJMD_TRY(prepare_graphs(c, todo)); // the caller prepared the graphs of an unsplit run
+        LJMD_TRY(run_steps_segment(c, todo));
+        c->pw.steps_since_sort += todo;
+        left -= todo;
+        if (c->pw.steps_since_sort >= iv) LJMD_TRY(resort_allpairs(c));
+    }
+    return LJMD_OK;
+}
+
+static int run_steps_segment(ljmd_ctx *c, int nsteps)
+{
     LJMD_TRY(launch_drift(c, 0, 1)); // r(t+dt) of the first step
     int done = 0;
     if (c->timing) {

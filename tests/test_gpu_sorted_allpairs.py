@@ -141,3 +141,36 @@ def test_sorted_ragged_size(lj, O):
     assert_forces_close((got.ax, got.ay, got.az), (ax, ay, az), scale, TOL)
     for g_, w_ in zip(obs, (e, d_, dd)):
         assert abs(g_ - w_) <= TOL * abs(w_)
+
+
+def test_sorted_resort_points_depend_on_the_step_count_only(lj, O, liquid):
+    """The periodic re-sort (LJMD_SORT_INTERVAL steps after the last complete upload) changes the resident order,
+    hence the summation order, hence the last bits -- but WHEN it happens depends on the step count alone:
+    10 steps in one call and in calls of 3 + 1 + 6 are bitwise equal, and both stay within 1e-11 of a run that
+    never re-sorts (and of the oracle)."""
+    p_o, s, _, _, _ = liquid
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    outs = []
+    for interval, calls in ((4, (10,)), (4, (3, 1, 6)), (0, (10,))):
+        os.environ["LJMD_SORT_INTERVAL"] = str(interval)
+        try:
+            with lj.Context(p, method=lj.METHOD_ALLPAIRS, flags=lj.FLAG_TRACK_UNWRAPPED) as ctx:
+                ctx.upload(_state(lj, s))
+                for m in calls:
+                    obs = ctx.step(m)
+                d = ctx.download()
+                ru = ctx.download_unwrapped()
+                outs.append((np.array(obs), [a.copy() for a in d.arrays()] + [a.copy() for a in ru]))
+        finally:
+            del os.environ["LJMD_SORT_INTERVAL"]
+    assert np.array_equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert np.array_equal(a, b)
+    assert np.all(np.abs(outs[0][0] - outs[2][0]) <= 1e-11 * np.abs(outs[2][0]))
+    for a, b in zip(outs[0][1], outs[2][1]):
+        assert rel_err(a, b) <= 1e-11
+    ref = [a.copy() for a in s]
+    for _ in range(10):
+        ref_obs = O.verlet_step(p_o, ref, cells=True)
+    assert np.all(np.abs(outs[0][0] - np.array(ref_obs)) <= 1e-10 * np.abs(np.array(ref_obs)))
+    assert rel_err(outs[0][1][0], ref[0]) <= 1e-10
