@@ -195,8 +195,11 @@ static int resort_allpairs(ljmd_ctx *c)
 
 static long long sort_interval()
 {
-    const char *e = getenv("LJMD_SORT_INTERVAL"); // steps between re-sorts; <= 0: never
-    return e ? atoll(e) : 2000;
+    // steps between re-sorts; <= 0: never.  A re-sort costs ~3 ms of host work at N = 32k (6 us per step at the
+    // default) and a freshly sorted liquid runs the force kernel 7 % faster than the order of a lattice start
+    // (0.432 vs 0.466 ms, profiles/r2_bench_cfg3_allpairs_resort50.json).
+    const char *e = getenv("LJMD_SORT_INTERVAL");
+    return e ? atoll(e) : 500;
 }
 
 static int enqueue_force(ljmd_ctx *c, int buf)
