@@ -1036,6 +1036,21 @@ __global__ void __launch_bounds__(256) nl_to_orig_kernel(int n, int narr, NlArgs
     for (int q = 0; q < narr; ++q) dst[(size_t)q * n + o] = a.arr[q][k];
 }
 
+// src = [r(3) | v(3) | a(3)][n] in ORIGINAL order -> the resident (cell-sorted) arrays, positions into rb[cur].
+__global__ void __launch_bounds__(256) nl_from_orig_kernel(int n, NlArgs a, const double *src, int cur)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int o = a.orig[k];
+    double *r = a.rb[cur];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        r[(size_t)c * n + k] = src[(size_t)c * n + o];
+        a.v[(size_t)c * n + k] = src[(size_t)(3 + c) * n + o];
+        a.a[(size_t)c * n + k] = src[(size_t)(6 + c) * n + o];
+    }
+}
+
 __global__ void __launch_bounds__(256) nl_identity_kernel(int n, int *orig, int *slot_of_orig)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1502,6 +1517,21 @@ int nlist_gather_orig(ljmd_ctx *c)
     for (int k = 0; k < 3; ++k) a.arr[q++] = c->st.ax + k * nn;
     if (c->st.rux) for (int k = 0; k < 3; ++k) a.arr[q++] = c->st.rux + k * nn;
     nl_to_orig_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, q, a, w.alt);
+    c->launches++;
+    LJMD_CUDA_CHECK(cudaGetLastError());
+    return LJMD_OK;
+}
+
+// The drop-in call keeps the cell-sorted order and the neighbour list of the previous call: the caller's arrays
+// (original order, already copied to w.alt as [r | v | a]) are scattered into the resident order.  Whether the
+// list is still good for them is decided by the usual skin test of the drift that follows (displacement of
+// r(t+dt) from the build positions): consecutive calls of an MD loop reuse the list ~40 times, anything else
+// (another configuration, permuted atoms) moves some atom by more than skin/2 and triggers a rebuild.
+int nlist_load_from_orig(ljmd_ctx *c)
+{
+    const int n = c->sc.n;
+    const NlArgs a = make_args(c, 0);
+    nl_from_orig_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, a, c->nw.alt, c->nw.cur_host);
     c->launches++;
     LJMD_CUDA_CHECK(cudaGetLastError());
     return LJMD_OK;

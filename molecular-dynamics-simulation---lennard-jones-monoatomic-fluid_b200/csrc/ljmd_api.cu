@@ -1067,6 +1067,7 @@ int compat_ctx(const ljmd_params *p, const char *who, ljmd_ctx **out)
         g_compat->p = *p;
         refresh_constants(g_compat);
         drop_graphs(g_compat);
+        g_compat->nw.compat_keep = false; // the list was built for other parameters
     }
     *out = g_compat;
     return LJMD_OK;
@@ -1103,6 +1104,9 @@ extern "C" int ljmd_compute_lj(const ljmd_params *params, const double *rx, cons
     LJMD_TRY(g.enter(c->device));
     LJMD_TRY(ensure_stage(c));
     const size_t nb = sizeof(double) * c->nR;
+    const bool keep_after = c->nw.compat_keep; // a successful force call leaves a consistent sorted state behind
+    c->nw.compat_keep = false;
+    (void)keep_after;
     const double *in3[3] = {rx, ry, rz};
     double *out3[3] = {ax, ay, az};
     bool direct = true;
@@ -1127,6 +1131,7 @@ extern "C" int ljmd_compute_lj(const ljmd_params *params, const double *rx, cons
         LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
         *epot = c->h_obs[0]; *d_epot = c->h_obs[2]; *dd_epot = c->h_obs[3];
         if (c->method == LJMD_METHOD_NLIST) LJMD_TRY(nlist_check_overflow(c));
+        c->nw.compat_keep = c->method == LJMD_METHOD_NLIST;
         return LJMD_OK;
     }
     memcpy(c->h_stage, rx, nb);
@@ -1155,6 +1160,7 @@ extern "C" int ljmd_compute_lj(const ljmd_params *params, const double *rx, cons
     const double *o = c->h_stage + 9 * c->nR;
     *epot = o[0]; *d_epot = o[2]; *dd_epot = o[3];
     if (c->method == LJMD_METHOD_NLIST) LJMD_TRY(nlist_check_overflow(c));
+    c->nw.compat_keep = c->method == LJMD_METHOD_NLIST;
     return LJMD_OK;
 }
 
@@ -1179,12 +1185,19 @@ extern "C" int ljmd_verlet_step(const ljmd_params *params, double *rx, double *r
     double *arr[9] = {rx, ry, rz, vx, vy, vz, ax, ay, az};
     bool direct = true; // large arrays: copy straight from / to the caller's (now page-locked) arrays
     for (int k = 0; k < 9; ++k) direct = compat_pin(arr[k], nb) && direct;
+    // LJMD_COMPAT_KEEP_LIST=0: re-sort and rebuild the neighbour list in every call (the behaviour of round 1)
+    const char *keep_env = getenv("LJMD_COMPAT_KEEP_LIST");
+    const bool keep_enabled = !(keep_env && atoi(keep_env) == 0);
+    const bool keep = c->method == LJMD_METHOD_NLIST && keep_enabled && c->nw.compat_keep;
+    c->nw.compat_keep = false; // until this call has gone through
     if (direct) {
+        double *h2d_dst = keep ? c->nw.alt : c->state_block;
         for (int k = 0; k < 9; ++k)
-            LJMD_CUDA_CHECK(cudaMemcpyAsync(c->state_block + (size_t)k * c->nR, arr[k], nb, cudaMemcpyHostToDevice, c->stream));
+            LJMD_CUDA_CHECK(cudaMemcpyAsync(h2d_dst + (size_t)k * c->nR, arr[k], nb, cudaMemcpyHostToDevice, c->stream));
         const double *dev_src = c->state_block;
         if (c->method == LJMD_METHOD_NLIST) {
-            LJMD_TRY(nlist_reset_identity(c));
+            if (keep) LJMD_TRY(nlist_load_from_orig(c));
+            else LJMD_TRY(nlist_reset_identity(c));
             LJMD_TRY(nlist_enqueue_drift(c));
             LJMD_TRY(nlist_enqueue_step(c));
             LJMD_TRY(nlist_gather_orig(c)); // r(t+dt), v, a back in original order
@@ -1198,6 +1211,7 @@ extern "C" int ljmd_verlet_step(const ljmd_params *params, double *rx, double *r
         LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_obs, c->fw.obs, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
         LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
         if (c->method == LJMD_METHOD_NLIST) LJMD_TRY(nlist_check_overflow(c));
+        c->nw.compat_keep = true;
         *epot = c->h_obs[0]; *ekin = c->h_obs[1]; *d_epot = c->h_obs[2]; *dd_epot = c->h_obs[3];
         return LJMD_OK;
     }
@@ -1237,9 +1251,10 @@ extern "C" int ljmd_verlet_step(const ljmd_params *params, double *rx, double *r
         *epot = og[0]; *ekin = og[1]; *d_epot = og[2]; *dd_epot = og[3];
         return LJMD_OK;
     }
-    LJMD_CUDA_CHECK(cudaMemcpyAsync(c->state_block, c->h_stage, 9 * nb, cudaMemcpyHostToDevice, c->stream));
+    LJMD_CUDA_CHECK(cudaMemcpyAsync(keep ? c->nw.alt : c->state_block, c->h_stage, 9 * nb, cudaMemcpyHostToDevice, c->stream));
     if (c->method == LJMD_METHOD_NLIST) {
-        LJMD_TRY(nlist_reset_identity(c));
+        if (keep) LJMD_TRY(nlist_load_from_orig(c));
+        else LJMD_TRY(nlist_reset_identity(c));
         LJMD_TRY(nlist_enqueue_drift(c));
         LJMD_TRY(nlist_enqueue_step(c));
         LJMD_TRY(nlist_gather_orig(c)); // r(t+dt), v, a back in original order
@@ -1254,6 +1269,7 @@ extern "C" int ljmd_verlet_step(const ljmd_params *params, double *rx, double *r
     }
     LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     if (c->method == LJMD_METHOD_NLIST) LJMD_TRY(nlist_check_overflow(c));
+    c->nw.compat_keep = true;
     for (int k = 0; k < 9; ++k) memcpy(arr[k], c->h_stage + (size_t)k * c->nR, nb);
     const double *o = c->h_stage + 9 * c->nR;
     *epot = o[0]; *ekin = o[1]; *d_epot = o[2]; *dd_epot = o[3];

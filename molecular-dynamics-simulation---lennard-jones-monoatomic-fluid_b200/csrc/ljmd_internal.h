@@ -159,6 +159,7 @@ struct NlistWork {
     int tpa;             // lanes per atom of the step kernel (1 or 4)
     int pipe;            // software-pipelined gathers (small systems)
     int cur_host;        // host mirror of NlCtl::cur
+    bool compat_keep;    // drop-in calls: the order and list left by the previous call can be reused
     long long rebuilds_host, rebuilds_counted;
     int *cell_of_slot, *cell_count, *cell_start, *cell_cursor, *tile_sum;
     unsigned long long *keys;
@@ -271,6 +272,7 @@ int nlist_capture_graph(ljmd_ctx *c, int nsteps, cudaGraphExec_t *out);
 int nlist_gather_orig(ljmd_ctx *c);         // state in original order -> nw.alt [r v a (ru)]
 int nlist_canonicalize(ljmd_ctx *c);
 int nlist_reset_identity(ljmd_ctx *c);
+int nlist_load_from_orig(ljmd_ctx *c);      // w.alt = [r | v | a] in original order -> resident order (drop-in calls)
 int nlist_check_overflow(ljmd_ctx *c);
 int nlist_pair_counts(ljmd_ctx *c, unsigned long long *d_counts);
 int nlist_download_cells(ljmd_ctx *c, int32_t *cell_of_atom, int32_t *cell_start, int32_t *order);

@@ -394,3 +394,41 @@ def test_nlist_slab_flag_wait_is_bounded_and_poison_halts(lj, O):
         finally:
             for c in ctxs:
                 c.close()
+
+
+def test_drop_in_call_keeps_the_list_between_calls(lj, O):
+    """Consecutive ljmd_verlet_step calls (host arrays in / out, AUTO -> neighbour list) reuse the cell-sorted order
+    and the list of the previous call; the skin test of the drift decides when to rebuild.  Every call is one
+    reference verlet_step from the state it was given: checked at 1e-12 on the first calls, late in a list's life
+    and right after a rebuild, and for a caller that suddenly passes a different configuration."""
+    p_o, st = make_config(O, "cfg3")
+    s0 = melt(O, p_o, st, 10, cells=True)
+    p = lj.SimParams.from_buffer_copy(bytes(p_o))
+    s = _state(lj, s0)
+    lj.compat_release()
+    check_at = {0, 1, 2, 30, 44, 45, 46, 47, 59}
+    for call in range(60):
+        before = [a.copy() for a in s.arrays()] if call in check_at else None
+        obs = lj.verlet_step(p, s)
+        if before is not None:
+            ref_obs = O.verlet_step(p_o, before, cells=True)
+            for got, want in zip(obs, ref_obs):
+                assert abs(got - want) <= TOL * abs(want), call
+            for k in range(3):
+                assert np.array_equal(s.arrays()[k], before[k]), call
+                assert rel_err(s.arrays()[3 + k], before[3 + k]) <= TOL, call
+                assert rel_err(s.arrays()[6 + k], before[6 + k]) <= TOL, call
+    # another configuration with the same n: the kept list is useless, the skin test must notice
+    other = melt(O, p_o, st, 3, cells=True)
+    perm = np.random.default_rng(0).permutation(p_o.n)
+    other = [np.ascontiguousarray(a[perm]) for a in other]
+    s2 = _state(lj, other)
+    ref = [a.copy() for a in other]
+    ref_obs = O.verlet_step(p_o, ref, cells=True)
+    obs = lj.verlet_step(p, s2)
+    for got, want in zip(obs, ref_obs):
+        assert abs(got - want) <= TOL * abs(want)
+    for k in range(3):
+        assert np.array_equal(s2.arrays()[k], ref[k])
+        assert rel_err(s2.arrays()[6 + k], ref[6 + k]) <= TOL
+    lj.compat_release()
