@@ -8,12 +8,15 @@ relative to /root/reference/scripts/md_one_run_analysis.py):
   :492-513  diffusion_from_msd_linear_fit :516-534  diffusion_from_vacf_integral
   :537-598  compute_rdf
 
-PARITY UNPINNED: the reference ships no expected outputs for these functions, and executing the
-reference script in the build container was not authorised, so nothing here was compared with
-output of the reference itself.  The restatement keeps the reference's numpy expressions
-(operation order, np.rint, true division, np.mean's pairwise sum, astype(int) truncation) so that
-it computes the same floating-point values; it is pinned by the known answers in
-tests/test_analysis_oracle.py (lattice shell counts, ballistic MSD, ideal-gas g(r) = 1).
+PARITY PINNED AGAINST THE REFERENCE ITSELF: the reference here is Python, so its own functions were run
+in the build container by tests/golden/make_golden_analysis.py (module imported with matplotlib stubbed;
+np.trapz aliased to np.trapezoid for numpy 2.x) and their outputs committed as
+tests/golden/analysis_ref.npz together with the inputs.  tests/test_analysis_golden.py checks every
+function below against that fixture: bit-identical on the numpy it was made with (asserted: g(r), the
+bin centres and the rva.dat arrays exactly, MSD / VACF within 1e-15 relative).  The restatement keeps the
+reference's numpy expressions (operation order, np.rint, true division, np.mean's pairwise sum,
+astype(int) truncation); tests/test_analysis_oracle.py adds known answers (lattice shell counts,
+ballistic MSD, ideal-gas g(r) = 1).
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline leg may import this module.
 """

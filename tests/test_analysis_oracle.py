@@ -2,8 +2,8 @@
 against known answers, of the rva.dat writer against an independent reader, and of the host-side
 pieces of the product mirror (analysis.py).
 
-PARITY UNPINNED: nothing here is output of the reference's md_one_run_analysis.py itself (it ships no
-expected outputs and executing it in the build container was not authorised)."""
+The comparison with OUTPUT OF THE REFERENCE'S OWN md_one_run_analysis.py is tests/test_analysis_golden.py
+(fixture tests/golden/analysis_ref.npz); the tests here are the independent known answers."""
 import importlib
 import struct
 

@@ -161,3 +161,53 @@ def test_tiled_time_correlation_is_bit_identical_to_the_default_kernel(an, A, n_
         del os.environ["LJMD_CORR_TILED"]
     assert np.array_equal(got_m, want_m) and np.array_equal(got_v, want_v)
     assert np.allclose(got_m, A.compute_msd_tau_timeorig(*ru, max_lag=max_lag, origin_stride=stride), rtol=RTOL, atol=0.0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Against OUTPUT OF THE REFERENCE ITSELF: tests/golden/analysis_ref.npz (made by
+# tests/golden/make_golden_analysis.py, which runs md_one_run_analysis.py's own functions)
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def G():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "analysis_ref.npz"))
+
+
+def test_rdf_kernel_equals_the_reference_output(an, G):
+    # g(r) = 2 c / norm with integer pair counts c from the kernel: equal to the reference's g TO THE BIT
+    L = float(G["liquid_header"][1])
+    pos = [G["liquid_r" + c] for c in "xyz"]
+    r, g = an.compute_rdf(*pos, L)
+    assert np.array_equal(r, G["liquid_rdf_r"]) and np.array_equal(g, G["liquid_rdf_g"])
+    r, g = an.compute_rdf(*pos, L, nbins=64, rmax=2.0)
+    assert np.array_equal(r, G["liquid_rdf64_r"]) and np.array_equal(g, G["liquid_rdf64_g"])
+    r, g = an.compute_rdf(G["gas864_x"], G["gas864_y"], G["gas864_z"], float(G["gas864_L"]), nbins=50)
+    assert np.array_equal(r, G["gas864_rdf_r"]) and np.array_equal(g, G["gas864_rdf_g"])
+    r, g = an.compute_rdf(G["many_x"], G["many_y"], G["many_z"], float(G["many_L"]), nbins=25)
+    assert np.array_equal(r, G["many_rdf_r"]) and np.array_equal(g, G["many_rdf_g"])
+
+
+@pytest.mark.parametrize("traj,tag,kw", [
+    ("liquid", "full", {}), ("liquid", "lag7_stride3", dict(max_lag=7, origin_stride=3)),
+    ("liquid", "lag100_stride2", dict(max_lag=100, origin_stride=2)),
+    ("walk", "full", {}), ("walk", "lag20_stride4", dict(max_lag=20, origin_stride=4)), ("walk", "lag0", dict(max_lag=0)),
+])
+def test_msd_vacf_kernels_equal_the_reference_output(an, G, traj, tag, kw):
+    if traj == "liquid":
+        ru, v = [G["liquid_ru" + c] for c in "xyz"], [G["liquid_v" + c] for c in "xyz"]
+    else:
+        ru, v = G["walk_ru"], G["walk_v"]
+    msd = an.compute_msd_tau_timeorig(*ru, **kw)
+    vacf = an.compute_vacf_tau_timeorig(*v, **kw)
+    want_m, want_v = G[f"{traj}_msd_{tag}"], G[f"{traj}_vacf_{tag}"]
+    assert msd.shape == want_m.shape and vacf.shape == want_v.shape
+    assert np.allclose(msd, want_m, rtol=RTOL, atol=0.0)
+    # VACF crosses zero: absolute floor of 1e-12 x VACF(0)
+    assert np.allclose(vacf, want_v, rtol=RTOL, atol=RTOL * abs(float(G[f"{traj}_vacf_full"][0])))
+
+
+def test_msd_vacf_kernels_short_inputs_equal_the_reference_output(an, G):
+    for ns in (1, 2):
+        ru = [G["liquid_ru" + c][:ns] for c in "xyz"]
+        v = [G["liquid_v" + c][:ns] for c in "xyz"]
+        assert np.allclose(an.compute_msd_tau_timeorig(*ru), G[f"liquid_msd_first{ns}"], rtol=RTOL, atol=0.0)
+        assert np.allclose(an.compute_vacf_tau_timeorig(*v), G[f"liquid_vacf_first{ns}"], rtol=RTOL, atol=0.0)
