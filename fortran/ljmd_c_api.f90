@@ -3,7 +3,7 @@
 !
 ! NOTE: this image has no Fortran compiler (no gfortran/flang/f951), so these three files are
 ! source-only here; they are deliberately tiny and mechanical.  The same C ABI is exercised from
-! C++ (host/md_driver.cpp) and Python (ctypes) in the test-suite.
+! C++ (examples/md_driver.cpp) and Python (ctypes) in the test-suite.
 !******************************************************************************************************
 module ljmd_c_api
   use, intrinsic :: iso_c_binding
