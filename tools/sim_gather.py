@@ -81,13 +81,28 @@ def analyse(n, L, pos, rl, sub, label):
     # per-atom requests are also issued for the padded group tail; ignored here
     out = {"label": label, "sub": sub, "entries_per_atom": len(si) / n, "sectors_per_request": sect / nreq,
            "lines_per_request": line / nreq, "requests_per_warp": nreq / ((n + 31) // 32)}
-    # union lists of clusters of 2 and 4 consecutive slots
+    # union lists of clusters of 2 and 4 consecutive slots; the union is walked in ascending slot order.
+    #   "lanes": the c lanes of a cluster read the same entry at the same time (a warp = 32/c clusters);
+    #   "thread": one thread per cluster (a warp = 32 clusters)
     for c in (2, 4):
         cl = si // c
-        u = len(np.unique(cl * (2 * n) + sj))
+        key = np.unique(cl * (2 * n) + sj)
+        ucl, usj = key // (2 * n), key % (2 * n)
         ncl = (n + c - 1) // c
-        out[f"union{c}_per_cluster"] = u / ncl
-        # warp = 32 clusters, request m = m-th entry of the union list (sorted the same way: by first occurrence order ~ slot)
+        out[f"union{c}_per_cluster"] = len(key) / ncl
+        ucnt = np.bincount(ucl, minlength=ncl)
+        ustart = np.concatenate([[0], np.cumsum(ucnt)])
+        um = np.arange(len(key)) - ustart[ucl]
+        for name, per_warp in (("lanes", 32 // c), ("thread", 32)):
+            w = ucl // per_warp
+            rq = w * 1024 + um
+            nrq = len(np.unique(rq))
+            ln = len(np.unique(rq * (2 * n) + usj // 4))
+            nwarps = (ncl + per_warp - 1) // per_warp
+            atoms_per_warp = per_warp * c
+            out[f"u{c}_{name}_lines_per_req"] = ln / nrq
+            out[f"u{c}_{name}_lines_per_atom"] = ln / n
+    out["lines_per_atom_now"] = line / n
     return out
 
 
@@ -96,7 +111,7 @@ def main():
     kinds = sys.argv[2:] or ["jitter", "liquid", "shuffled"]
     for kind in kinds:
         n, L, pos = state(k, kind)
-        for sub in ("orig", "z", "morton1", "morton2", "morton3"):
+        for sub in ("orig", "morton1"):
             r = analyse(n, L, pos, 2.8, sub, kind)
             print({k_: (round(v, 2) if isinstance(v, float) else v) for k_, v in r.items()}, flush=True)
 
