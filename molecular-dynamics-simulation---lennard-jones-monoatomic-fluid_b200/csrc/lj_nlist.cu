@@ -1351,6 +1351,9 @@ void nlist_free(ljmd_ctx *c)
     cudaFree(w.flags);
     cudaFree(w.sl_rng);
     if (w.side_stream) cudaStreamDestroy(w.side_stream);
+    cudaFree(w.compat_r);
+    if (w.ev_r_ready) cudaEventDestroy(w.ev_r_ready);
+    if (w.ev_r_copied) cudaEventDestroy(w.ev_r_copied);
 }
 
 // Host-side write of selected NlCtl fields (stream-ordered).
@@ -1517,6 +1520,52 @@ int nlist_gather_orig(ljmd_ctx *c)
     for (int k = 0; k < 3; ++k) a.arr[q++] = c->st.ax + k * nn;
     if (c->st.rux) for (int k = 0; k < 3; ++k) a.arr[q++] = c->st.rux + k * nn;
     nl_to_orig_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, q, a, w.alt);
+    c->launches++;
+    LJMD_CUDA_CHECK(cudaGetLastError());
+    return LJMD_OK;
+}
+
+// Drop-in calls with page-locked caller arrays (large systems; the call is PCIe bound: 75 MB each way at N = 2^20
+// against 0.3 ms of kernels).  r(t+dt) is final as soon as the drift has run -- BEFORE the force / kick kernel --
+// so it is gathered into its own buffer (original order; w.alt is the permutation scratch of a list rebuild that
+// the step may trigger, so it cannot be used) and its device-to-host copies run on the side stream while the
+// main stream computes the step; v and a follow on the main stream afterwards.  Called between the drift and the
+// step: rb[1 - cur] holds r(t+dt) and `orig` is the table of the order it is stored in (a rebuild inside the step
+// changes both, after this gather in stream order).  The caller makes the main stream wait for ev_r_copied.
+// Measured at N = 2^20 (profiles/r2_e2e_overlap.txt): 3.36 -> 3.15 ms per call on one box, 2.89 ms on another.  Going
+// further -- upload, drift and this download pipelined over 4 / 8 chunks of atoms, PCIe in both directions at once --
+// was built, bitwise equal, and SLOWER (3.16 / 3.36 ms against 2.89 ms on the same box): 12 more copies per chunk at
+// ~7 us of fixed cost each outweigh the hidden 0.46 ms.  Removed again.
+int nlist_early_positions_d2h(ljmd_ctx *c, double *const host_r[3])
+{
+    NlistWork &w = c->nw;
+    const int n = c->sc.n;
+    const size_t nn = c->nR, bytes = sizeof(double) * nn;
+    if (!w.compat_r) LJMD_CUDA_CHECK(cudaMalloc(&w.compat_r, 3 * bytes));
+    if (!w.ev_r_ready) LJMD_CUDA_CHECK(cudaEventCreateWithFlags(&w.ev_r_ready, cudaEventDisableTiming));
+    if (!w.ev_r_copied) LJMD_CUDA_CHECK(cudaEventCreateWithFlags(&w.ev_r_copied, cudaEventDisableTiming));
+    NlArgs a = make_args(c, 0);
+    for (int k = 0; k < 3; ++k) a.arr[k] = c->rbuf[1 - w.cur_host] + k * nn;
+    nl_to_orig_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, 3, a, w.compat_r);
+    c->launches++;
+    LJMD_CUDA_CHECK(cudaGetLastError());
+    LJMD_CUDA_CHECK(cudaEventRecord(w.ev_r_ready, c->stream));
+    LJMD_CUDA_CHECK(cudaStreamWaitEvent(w.side_stream, w.ev_r_ready, 0));
+    for (int k = 0; k < 3; ++k)
+        LJMD_CUDA_CHECK(cudaMemcpyAsync(host_r[k], w.compat_r + (size_t)k * nn, bytes, cudaMemcpyDeviceToHost, w.side_stream));
+    LJMD_CUDA_CHECK(cudaEventRecord(w.ev_r_copied, w.side_stream));
+    return LJMD_OK;
+}
+
+// v and a in ORIGINAL order into w.alt[3..8] (the layout of nlist_gather_orig without the positions).
+int nlist_gather_orig_va(ljmd_ctx *c)
+{
+    const int n = c->sc.n;
+    const size_t nn = c->nR;
+    NlArgs a = make_args(c, 0);
+    for (int k = 0; k < 3; ++k) a.arr[k] = c->st.vx + k * nn;
+    for (int k = 0; k < 3; ++k) a.arr[3 + k] = c->st.ax + k * nn;
+    nl_to_orig_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, 6, a, c->nw.alt + 3 * nn);
     c->launches++;
     LJMD_CUDA_CHECK(cudaGetLastError());
     return LJMD_OK;

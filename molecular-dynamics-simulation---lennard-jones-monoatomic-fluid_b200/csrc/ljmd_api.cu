@@ -1191,24 +1191,33 @@ extern "C" int ljmd_verlet_step(const ljmd_params *params, double *rx, double *r
     const bool keep = c->method == LJMD_METHOD_NLIST && keep_enabled && c->nw.compat_keep;
     c->nw.compat_keep = false; // until this call has gone through
     if (direct) {
+        const double *dev_src = c->state_block;
+        // LJMD_COMPAT_OVERLAP=0: download r(t+dt) after the step with v and a (the behaviour before the overlap)
+        static const bool overlap = !(getenv("LJMD_COMPAT_OVERLAP") && atoi(getenv("LJMD_COMPAT_OVERLAP")) == 0);
+        int first_out = 0; // first array still to be copied to the caller on the main stream
         double *h2d_dst = keep ? c->nw.alt : c->state_block;
         for (int k = 0; k < 9; ++k)
             LJMD_CUDA_CHECK(cudaMemcpyAsync(h2d_dst + (size_t)k * c->nR, arr[k], nb, cudaMemcpyHostToDevice, c->stream));
-        const double *dev_src = c->state_block;
         if (c->method == LJMD_METHOD_NLIST) {
             if (keep) LJMD_TRY(nlist_load_from_orig(c));
             else LJMD_TRY(nlist_reset_identity(c));
             LJMD_TRY(nlist_enqueue_drift(c));
+            if (overlap) { // r(t+dt) is final now: its download overlaps the force / kick kernel
+                LJMD_TRY(nlist_early_positions_d2h(c, arr));
+                first_out = 3;
+            }
             LJMD_TRY(nlist_enqueue_step(c));
-            LJMD_TRY(nlist_gather_orig(c)); // r(t+dt), v, a back in original order
+            if (first_out) LJMD_TRY(nlist_gather_orig_va(c)); // v, a back in original order
+            else LJMD_TRY(nlist_gather_orig(c));              // r(t+dt), v, a back in original order
             dev_src = c->nw.alt;
         } else {
             LJMD_TRY(launch_drift(c, 0, 1));
             LJMD_TRY(enqueue_step(c, 0, 2));
         }
-        for (int k = 0; k < 9; ++k)
+        for (int k = first_out; k < 9; ++k)
             LJMD_CUDA_CHECK(cudaMemcpyAsync(arr[k], dev_src + (size_t)k * c->nR, nb, cudaMemcpyDeviceToHost, c->stream));
         LJMD_CUDA_CHECK(cudaMemcpyAsync(c->h_obs, c->fw.obs, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (first_out) LJMD_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->nw.ev_r_copied, 0));
         LJMD_CUDA_CHECK(cudaStreamSynchronize(c->stream));
         if (c->method == LJMD_METHOD_NLIST) LJMD_TRY(nlist_check_overflow(c));
         c->nw.compat_keep = true;

@@ -173,7 +173,9 @@ struct NlistWork {
     double *mom;         // [3] momentum of the atoms handled by the last step launch
     double4 *p4;         // [2][n] packed positions (x, y, z, 0) of the two position buffers
     NlCtl *ctl;
-    cudaStream_t side_stream; // captures the IF-node bodies of the step graph
+    cudaStream_t side_stream; // captures the IF-node bodies of the step graph; carries the early position download of drop-in calls
+    double *compat_r;         // [3][n] r(t+dt) in original order, gathered right after the drift of a drop-in call (lazily allocated)
+    cudaEvent_t ev_r_ready, ev_r_copied; // drop-in calls: compat_r written (main stream) / copied to the caller (side stream)
     // slab sharding over the GPUs of a node
     int sh_on, rank, world, xlo, xhi, own_blocks;
     double4 *peer_p4[LJMD_MAX_RANKS];
@@ -270,6 +272,8 @@ int nlist_enqueue_step(ljmd_ctx *c);        // rebuild-if-needed + fused step ke
 int nlist_enqueue_step_kernel(ljmd_ctx *c); // the fused step kernel alone
 int nlist_capture_graph(ljmd_ctx *c, int nsteps, cudaGraphExec_t *out);
 int nlist_gather_orig(ljmd_ctx *c);         // state in original order -> nw.alt [r v a (ru)]
+int nlist_early_positions_d2h(ljmd_ctx *c, double *const host_r[3]); // drop-in calls: r(t+dt) to the caller while the step kernel runs
+int nlist_gather_orig_va(ljmd_ctx *c);      // v, a in original order -> nw.alt [. v a]
 int nlist_canonicalize(ljmd_ctx *c);
 int nlist_reset_identity(ljmd_ctx *c);
 int nlist_load_from_orig(ljmd_ctx *c);      // w.alt = [r | v | a] in original order -> resident order (drop-in calls)

@@ -3,6 +3,8 @@
 * the drop-in host-array call ljmd_verlet_step is replayed as one CUDA graph (upload, drift, force,
   finalize, download) by default; LJMD_COMPAT_GRAPH=0 issues the separate launches.  Both must be
   bitwise equal (first run on a B200 in round 2: green).
+* large systems: page-locked caller arrays vs the bounce buffer (LJMD_COMPAT_PIN), and the download of r(t+dt)
+  overlapped with the step kernel vs after it (LJMD_COMPAT_OVERLAP), across list rebuilds.
 """
 import os
 import subprocess
@@ -81,3 +83,43 @@ def test_page_locked_caller_arrays_are_bitwise_equal_to_the_bounce_buffer(tmp_pa
         outs.append(np.load(out))
     for key in ("obs", "state", "e0"):
         assert np.array_equal(outs[0][key], outs[1][key]), key
+
+
+_SCRIPT_LONG = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+import bench, ljmd_b200 as lj
+k = 32                                             # N = 131,072: the page-locked path
+L = k * (4.0 / 0.8) ** (1.0 / 3.0)
+w = dict(k=k, L=L, rc=2.5, dt=1e-3, method="nlist", T=1.0)
+n, arrs = bench.synthetic_state(w, seed=4)
+p = lj.init_params(n, L, 1e-3, 2.5, k)
+s = lj.SimState.from_arrays(arrs)
+lj.compute_lj_potential_energy(p, s)
+obs, snaps = [], []
+for call in range(70):                             # the list is rebuilt about every 42 calls at this dt and T
+    obs.append(lj.verlet_step(p, s))
+    if call in (0, 1, 40, 45, 50, 69):
+        snaps.append(np.array([getattr(s, nm) for nm in lj.SimState.NAMES]))
+lj.compat_release()
+np.savez(sys.argv[1], snaps=np.array(snaps), obs=np.array(obs))
+"""
+
+
+def test_overlapped_position_download_is_bitwise_equal_across_rebuilds(tmp_path):
+    """Large systems: r(t+dt) is final after the drift, so the drop-in call copies it to the caller on a second stream
+    while the force / kick kernel runs (LJMD_COMPAT_OVERLAP=0: after the step, with v and a).  70 consecutive calls
+    (at least one list rebuild inside a call) must agree bit for bit in every array the caller sees."""
+    outs = []
+    for name, env_extra in (("serial", {"LJMD_COMPAT_OVERLAP": "0"}), ("overlap", {})):
+        out = tmp_path / (name + ".npz")
+        env = dict(os.environ)
+        env.pop("LJMD_COMPAT_OVERLAP", None)
+        env.update(env_extra)
+        subprocess.run([sys.executable, "-c", _SCRIPT_LONG.format(root=ROOT), str(out)], check=True, env=env, timeout=240)
+        outs.append(np.load(out))
+    assert np.all(np.isfinite(outs[0]["obs"]))
+    for key in ("obs", "snaps"):
+        assert np.array_equal(outs[0][key], outs[1][key]), key
+    # the positions really moved between the snapshots (the test is not comparing a frozen state)
+    assert not np.array_equal(outs[0]["snaps"][0][:3], outs[0]["snaps"][-1][:3])
