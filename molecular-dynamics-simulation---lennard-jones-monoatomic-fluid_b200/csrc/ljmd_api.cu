@@ -1206,9 +1206,13 @@ extern "C" int ljmd_verlet_step(const ljmd_params *params, double *rx, double *r
                 LJMD_TRY(nlist_early_positions_d2h(c, arr));
                 first_out = 3;
             }
-            LJMD_TRY(nlist_enqueue_step(c));
-            if (first_out) LJMD_TRY(nlist_gather_orig_va(c)); // v, a back in original order
-            else LJMD_TRY(nlist_gather_orig(c));              // r(t+dt), v, a back in original order
+            int rc = nlist_enqueue_step(c);
+            if (rc == LJMD_OK) rc = first_out ? nlist_gather_orig_va(c) // v, a back in original order
+                                              : nlist_gather_orig(c);   // r(t+dt), v, a back in original order
+            if (rc != LJMD_OK) { // nothing may still be writing into the caller's arrays when the error is returned
+                if (first_out) cudaStreamSynchronize(c->nw.side_stream);
+                return rc;
+            }
             dev_src = c->nw.alt;
         } else {
             LJMD_TRY(launch_drift(c, 0, 1));
