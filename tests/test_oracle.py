@@ -177,6 +177,62 @@ def test_accelerations_are_minus_the_energy_gradient(O):
     assert checked >= 10
 
 
+def test_forces_and_sums_against_extended_precision_on_a_disordered_state(O):
+    """An independent restatement of lj_potential_energy.f90:109-223 in numpy `longdouble` (x87 80-bit: 64-bit
+    significand, 11 more bits than the oracle's arithmetic), vectorised over all i<j pairs, sharing no code with
+    the oracle: the formulas of the reference file, minimum image as d - L*rint(d/L), strict cutoff, tails.  On a
+    melted config-1 state the oracle's U, d_epot, dd_epot and every acceleration component must agree with it to
+    a few ulp of what was summed -- which bounds how far the checker itself is from exact arithmetic, and so how
+    much of the 1e-12 budget of the GPU parity tests the checker may use up (none worth mentioning)."""
+    ld = np.longdouble
+    if np.finfo(ld).nmant < 63:
+        pytest.skip("numpy longdouble is not the 80-bit extended type on this platform")
+    p, st = make_config(O, "cfg1")
+    s = melt(O, p, st, 400)
+    n, L, rc = p.n, ld(p.box_length), ld(p.rc)
+    x, y, z = (np.asarray(a, dtype=ld) for a in s[:3])
+    i, j = np.triu_indices(n, 1)
+    d = [c[i] - c[j] for c in (x, y, z)]
+    d = [c - L * np.rint(c / L) for c in d]
+    r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2]
+    # the cutoff decision is the reference's: taken on r2 in DOUBLE, in its operation order (:129,:132)
+    dd = [np.asarray(s[c])[i] - np.asarray(s[c])[j] for c in range(3)]
+    dd = [c - p.box_length * np.round(c * p.inv_box_length) for c in dd]
+    inside = ((dd[0] * dd[0] + dd[1] * dd[1]) + dd[2] * dd[2]) < p.rc_square
+    assert np.array_equal(inside, r2 < rc * rc)          # no pair within 1e-16 of the cutoff in this state
+    ir2 = 1 / r2[inside]
+    ir6 = ir2 * ir2 * ir2
+    ir12 = ir6 * ir6
+    du = -2 * ir12 + ir6
+    npd = ld(n)
+    pi = ld("3.1415926535897932384626433832795")
+    tail = 8 * pi * npd * npd / (ld(p.volume) * rc ** 3)
+    rc6 = rc ** 6
+    want_u = 4 * np.sum(ir12 - ir6) + tail * (1 / (3 * rc6) - 1) / 3
+    want_du = 24 * np.sum(du) + 2 * tail * (-2 / (3 * rc6) + 1)
+    want_ddu = 24 * np.sum(26 * ir12 - 7 * ir6) + 2 * tail * (26 / (3 * rc6) - 7)
+    acc = np.zeros((3, n), dtype=ld)
+    ii, jj = i[inside], j[inside]
+    for c in range(3):
+        f = -du * d[c][inside] * ir2
+        np.add.at(acc[c], ii, f)
+        np.add.at(acc[c], jj, -f)
+    acc *= 24
+    ax, ay, az, u, du_o, ddu_o = O.compute_lj(p, *s[:3])
+    # scales: the sums of the MAGNITUDES that were added up (cancellation-aware, like conftest.scalar_scales)
+    s12, s6 = float(np.sum(ir12)), float(np.sum(ir6))
+    eps = 2.0 ** -52
+    assert abs(ld(u) - want_u) <= 32 * eps * (4 * (s12 + s6) + 20)
+    assert abs(ld(du_o) - want_du) <= 32 * eps * (24 * (2 * s12 + s6) + 110)
+    assert abs(ld(ddu_o) - want_ddu) <= 32 * eps * (24 * (26 * s12 + 7 * s6) + 750)
+    mag = np.zeros(n, dtype=ld)
+    w = 24 * np.abs(du * ir2) * np.sqrt(r2[inside])
+    np.add.at(mag, ii, w)
+    np.add.at(mag, jj, w)
+    for got, want in zip((ax, ay, az), acc):
+        assert np.max(np.abs(np.asarray(got, dtype=ld) - want) / mag) <= 8 * eps
+
+
 def test_newton3_and_momentum(O):
     p, st = make_config(O, "cfg1")
     s = melt(O, p, st, 200)
