@@ -177,6 +177,45 @@ def test_accelerations_are_minus_the_energy_gradient(O):
     assert checked >= 10
 
 
+def _extended_lj(p, pos):
+    """lj_potential_energy.f90:109-223 restated in numpy longdouble over all i<j pairs (no code shared with the
+    oracle).  Returns (acc[3][n], U, d_epot, dd_epot, in-cutoff mask, pair-force magnitude scale per atom, S12, S6)."""
+    ld = np.longdouble
+    n, L, rc = p.n, ld(p.box_length), ld(p.rc)
+    x, y, z = (np.asarray(a, dtype=ld) for a in pos)
+    i, j = np.triu_indices(n, 1)
+    d = [c[i] - c[j] for c in (x, y, z)]
+    d = [c - L * np.rint(c / L) for c in d]
+    r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2]
+    inside = r2 < rc * rc
+    ir2 = 1 / r2[inside]
+    ir6 = ir2 * ir2 * ir2
+    ir12 = ir6 * ir6
+    du = -2 * ir12 + ir6
+    pi = ld("3.1415926535897932384626433832795")
+    tail = 8 * pi * ld(n) * ld(n) / (ld(p.volume) * rc ** 3)
+    rc6 = rc ** 6
+    u = 4 * np.sum(ir12 - ir6) + tail * (1 / (3 * rc6) - 1) / 3
+    d_u = 24 * np.sum(du) + 2 * tail * (-2 / (3 * rc6) + 1)
+    dd_u = 24 * np.sum(26 * ir12 - 7 * ir6) + 2 * tail * (26 / (3 * rc6) - 7)
+    acc = np.zeros((3, n), dtype=ld)
+    mag = np.zeros(n, dtype=ld)
+    ii, jj = i[inside], j[inside]
+    for c in range(3):
+        f = -du * d[c][inside] * ir2
+        np.add.at(acc[c], ii, f)
+        np.add.at(acc[c], jj, -f)
+    w = 24 * np.abs(du * ir2) * np.sqrt(r2[inside])
+    np.add.at(mag, ii, w)
+    np.add.at(mag, jj, w)
+    return 24 * acc, u, d_u, dd_u, (i, j, inside), mag, float(np.sum(ir12)), float(np.sum(ir6))
+
+
+def _need_extended():
+    if np.finfo(np.longdouble).nmant < 63:
+        pytest.skip("numpy longdouble is not the 80-bit extended type on this platform")
+
+
 def test_forces_and_sums_against_extended_precision_on_a_disordered_state(O):
     """An independent restatement of lj_potential_energy.f90:109-223 in numpy `longdouble` (x87 80-bit: 64-bit
     significand, 11 more bits than the oracle's arithmetic), vectorised over all i<j pairs, sharing no code with
@@ -184,53 +223,54 @@ def test_forces_and_sums_against_extended_precision_on_a_disordered_state(O):
     melted config-1 state the oracle's U, d_epot, dd_epot and every acceleration component must agree with it to
     a few ulp of what was summed -- which bounds how far the checker itself is from exact arithmetic, and so how
     much of the 1e-12 budget of the GPU parity tests the checker may use up (none worth mentioning)."""
+    _need_extended()
     ld = np.longdouble
-    if np.finfo(ld).nmant < 63:
-        pytest.skip("numpy longdouble is not the 80-bit extended type on this platform")
     p, st = make_config(O, "cfg1")
     s = melt(O, p, st, 400)
-    n, L, rc = p.n, ld(p.box_length), ld(p.rc)
-    x, y, z = (np.asarray(a, dtype=ld) for a in s[:3])
-    i, j = np.triu_indices(n, 1)
-    d = [c[i] - c[j] for c in (x, y, z)]
-    d = [c - L * np.rint(c / L) for c in d]
-    r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2]
+    acc, want_u, want_du, want_ddu, (i, j, inside), mag, s12, s6 = _extended_lj(p, s[:3])
     # the cutoff decision is the reference's: taken on r2 in DOUBLE, in its operation order (:129,:132)
     dd = [np.asarray(s[c])[i] - np.asarray(s[c])[j] for c in range(3)]
     dd = [c - p.box_length * np.round(c * p.inv_box_length) for c in dd]
-    inside = ((dd[0] * dd[0] + dd[1] * dd[1]) + dd[2] * dd[2]) < p.rc_square
-    assert np.array_equal(inside, r2 < rc * rc)          # no pair within 1e-16 of the cutoff in this state
-    ir2 = 1 / r2[inside]
-    ir6 = ir2 * ir2 * ir2
-    ir12 = ir6 * ir6
-    du = -2 * ir12 + ir6
-    npd = ld(n)
-    pi = ld("3.1415926535897932384626433832795")
-    tail = 8 * pi * npd * npd / (ld(p.volume) * rc ** 3)
-    rc6 = rc ** 6
-    want_u = 4 * np.sum(ir12 - ir6) + tail * (1 / (3 * rc6) - 1) / 3
-    want_du = 24 * np.sum(du) + 2 * tail * (-2 / (3 * rc6) + 1)
-    want_ddu = 24 * np.sum(26 * ir12 - 7 * ir6) + 2 * tail * (26 / (3 * rc6) - 7)
-    acc = np.zeros((3, n), dtype=ld)
-    ii, jj = i[inside], j[inside]
-    for c in range(3):
-        f = -du * d[c][inside] * ir2
-        np.add.at(acc[c], ii, f)
-        np.add.at(acc[c], jj, -f)
-    acc *= 24
+    assert np.array_equal(inside, ((dd[0] * dd[0] + dd[1] * dd[1]) + dd[2] * dd[2]) < p.rc_square)
     ax, ay, az, u, du_o, ddu_o = O.compute_lj(p, *s[:3])
     # scales: the sums of the MAGNITUDES that were added up (cancellation-aware, like conftest.scalar_scales)
-    s12, s6 = float(np.sum(ir12)), float(np.sum(ir6))
     eps = 2.0 ** -52
     assert abs(ld(u) - want_u) <= 32 * eps * (4 * (s12 + s6) + 20)
     assert abs(ld(du_o) - want_du) <= 32 * eps * (24 * (2 * s12 + s6) + 110)
     assert abs(ld(ddu_o) - want_ddu) <= 32 * eps * (24 * (26 * s12 + 7 * s6) + 750)
-    mag = np.zeros(n, dtype=ld)
-    w = 24 * np.abs(du * ir2) * np.sqrt(r2[inside])
-    np.add.at(mag, ii, w)
-    np.add.at(mag, jj, w)
     for got, want in zip((ax, ay, az), acc):
         assert np.max(np.abs(np.asarray(got, dtype=ld) - want) / mag) <= 8 * eps
+
+
+def test_verlet_step_against_extended_precision(O):
+    """verlet.f90:58-95 restated in longdouble around the extended-precision force routine: one step from a melted
+    state.  Positions agree to an ulp of the box length (one atom may land on the other side of a wrap, which the
+    comparison takes modulo L), velocities to 1e-15 of the thermal velocity, E_kin to 1e-14."""
+    _need_extended()
+    ld = np.longdouble
+    p, st = make_config(O, "cfg1")
+    s = melt(O, p, st, 400)
+    L, dt = ld(p.box_length), ld(p.dt)
+    r = [np.asarray(a, dtype=ld) for a in s[:3]]
+    v = [np.asarray(a, dtype=ld) for a in s[3:6]]
+    a0 = [np.asarray(a, dtype=ld) for a in s[6:9]]
+    rn = [(r[c] + v[c] * dt) + a0[c] * (dt * dt / 2) for c in range(3)]
+    rn = [c - L * np.floor(c / L) for c in rn]
+    vh = [v[c] + a0[c] * (dt / 2) for c in range(3)]
+    a1, want_u, _, _, _, mag, _, _ = _extended_lj(p, rn)
+    vn = [vh[c] + a1[c] * (dt / 2) for c in range(3)]
+    want_k = (np.sum(vn[0] ** 2) + np.sum(vn[1] ** 2) + np.sum(vn[2] ** 2)) / 2
+    got = [a.copy() for a in s]
+    obs = O.verlet_step(p, got)
+    eps = 2.0 ** -52
+    for c in range(3):
+        dr = np.asarray(got[c], dtype=ld) - rn[c]
+        dr = dr - L * np.rint(dr / L)
+        assert np.max(np.abs(dr)) <= 4 * eps * float(L)
+        assert np.max(np.abs(np.asarray(got[3 + c], dtype=ld) - vn[c])) <= 16 * eps * float(np.max(np.abs(vn[c])))
+        assert np.max(np.abs(np.asarray(got[6 + c], dtype=ld) - a1[c]) / mag) <= 8 * eps
+    assert abs(ld(obs[1]) - want_k) <= 64 * eps * float(want_k)
+    assert abs(ld(obs[0]) - want_u) <= 1e-13 * abs(float(want_u))
 
 
 def test_newton3_and_momentum(O):
